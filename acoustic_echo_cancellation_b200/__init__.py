@@ -1,0 +1,18 @@
+"""acoustic_echo_cancellation_b200 -- B200-native stage-1 linear echo canceller.
+
+Host side of the drop-in for the data-parallel hot path of
+SZU-Speech/Acoustic-Echo-Cancellation (STFT -> partitioned FDAF -> iSTFT -> feature
+output).  Importing the package does not load CUDA; the first call into
+``libaec_b200.so`` does, and raises if the library has not been built -- there is no
+CPU fallback.  See DESIGN.md / INTEGRATION.md.
+"""
+from ._lib import ALGO_KALMAN, ALGO_NLMS, AecError, LIB_PATH  # noqa: F401
+from .stage1 import (HostPipeline, Stage1Config, fp32_peak_tflops, launch_count, num_frames,  # noqa: F401
+                     out_samples, pinned_empty, stage1_aec)
+from .spectral import ConvSTFT, ConviSTFT, erb_filterbank, stage2_features  # noqa: F401
+
+__all__ = [
+    "ALGO_KALMAN", "ALGO_NLMS", "AecError", "LIB_PATH", "HostPipeline", "Stage1Config", "fp32_peak_tflops",
+    "launch_count", "num_frames", "out_samples", "pinned_empty", "stage1_aec", "ConvSTFT", "ConviSTFT",
+    "erb_filterbank", "stage2_features",
+]

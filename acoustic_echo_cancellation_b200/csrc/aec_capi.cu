@@ -1,0 +1,426 @@
+// C ABI of libaec_b200.so: configuration helpers, constant tables, the stage-1 entry points
+// (device- and host-buffer variants) and the FP32 peak probe used by bench.py.
+// Declarations and the reference seams each entry replaces: include/aec_b200.h.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "aec_common.cuh"
+#include "stage1_launch.cuh"
+
+namespace aec {
+
+// ------------------------------------------------------------------------------------------
+// error bookkeeping
+// ------------------------------------------------------------------------------------------
+static thread_local char g_cuda_err[256] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_cuda_error(cudaError_t e, const char* where) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e), where);
+}
+void count_launch(int n) { g_launches += n; }
+
+// ------------------------------------------------------------------------------------------
+// constant tables (per device)
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr int kMaxDevices = 64;
+struct DeviceTables {
+    bool ready = false;
+    Tables t{};
+};
+DeviceTables g_tables[kMaxDevices];
+std::mutex g_tables_mu;
+
+int build_tables(DeviceTables* dt) {
+    const double pi = 3.14159265358979323846;
+    std::vector<float2> tw256(256), tw512(129), win_a(256), win_s(256), win_r(256);
+    std::vector<float> hann(512);
+    for (int q = 0; q < 16; ++q)
+        for (int h = 0; h < 16; ++h) {
+            const double a = -2.0 * pi * double(h * q) / 256.0;
+            tw256[q * 16 + h] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int k = 0; k <= 128; ++k) {
+        const double a = -2.0 * pi * double(k) / 512.0;
+        tw512[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    std::vector<double> w(512);
+    for (int n = 0; n < 512; ++n) {
+        w[n] = 0.5 - 0.5 * cos(2.0 * pi * n / 512.0);   // scipy get_window('hann', 512, fftbins=True)
+        hann[n] = (float)w[n];
+    }
+    auto syn = [&](int n) {
+        // every kept output sample sums exactly two frames: coff = w[n']^2 + w[n'+256]^2
+        const int m = n & 255;
+        const double wf = (double)(float)w[m], wb = (double)(float)w[m + 256];
+        const double coff = wf * wf + wb * wb;
+        return (double)(float)w[n] / (512.0 * (coff + 1e-8));
+    };
+    for (int m = 0; m < 256; ++m) {
+        win_a[m] = make_float2((float)(0.5 * (double)(float)w[2 * m]), (float)(0.5 * (double)(float)w[2 * m + 1]));
+        win_s[m] = make_float2((float)syn(2 * m), (float)syn(2 * m + 1));
+        win_r[m] = make_float2((float)((double)(float)w[2 * m] / 512.0), (float)((double)(float)w[2 * m + 1] / 512.0));
+    }
+    char* dev = nullptr;
+    AEC_CUDA_CHECK(cudaMalloc(&dev, 16384));
+    size_t off = 0;
+    auto put = [&](const void* src, size_t n) -> const void* {
+        void* dst = dev + off;
+        cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+        off += (n + 255) / 256 * 256;
+        return dst;
+    };
+    dt->t.tw256 = (const float2*)put(tw256.data(), 256 * sizeof(float2));
+    dt->t.tw512 = (const float2*)put(tw512.data(), 129 * sizeof(float2));
+    dt->t.win_a = (const float2*)put(win_a.data(), 256 * sizeof(float2));
+    dt->t.win_s = (const float2*)put(win_s.data(), 256 * sizeof(float2));
+    dt->t.win_r = (const float2*)put(win_r.data(), 256 * sizeof(float2));
+    dt->t.hann512 = (const float*)put(hann.data(), 512 * sizeof(float));
+    AEC_CUDA_CHECK(cudaGetLastError());
+    dt->ready = true;
+    return AEC_OK;
+}
+}  // namespace
+
+int get_tables(Tables* out) {
+    int dev = -1;
+    AEC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return AEC_ENODEVICE;
+    std::lock_guard<std::mutex> lock(g_tables_mu);
+    if (!g_tables[dev].ready) {
+        cudaDeviceProp prop{};
+        AEC_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major != 10) {
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                     prop.major, prop.minor);
+            return AEC_ENODEVICE;
+        }
+        const int rc = build_tables(&g_tables[dev]);
+        if (rc != AEC_OK) return rc;
+    }
+    *out = g_tables[dev].t;
+    return AEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 peak probe: 8 independent FFMA chains per thread, every SM full
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = (float)threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = fmaf(r[i], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += r[i];
+    if (s == 123.456f) out[0] = s;   // never true; keeps the chains alive
+}
+
+}  // namespace aec
+
+using namespace aec;
+
+// ------------------------------------------------------------------------------------------
+// plain helpers
+// ------------------------------------------------------------------------------------------
+extern "C" int aec_version(void) { return AEC_B200_VERSION; }
+
+extern "C" const char* aec_strerror(int code) {
+    switch (code) {
+        case AEC_OK: return "ok";
+        case AEC_EINVAL: return "invalid argument";
+        case AEC_EUNSUPPORTED: return "frame/partitions/algo combination not built into libaec_b200";
+        case AEC_ECUDA: return "CUDA runtime error (see aec_last_cuda_error)";
+        case AEC_ENODEVICE: return "no usable sm_100 CUDA device is current";
+        case AEC_ENOMEM: return "out of memory";
+        default: return "unknown aec error";
+    }
+}
+
+extern "C" const char* aec_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" int aec_cfg_default(aec_cfg* cfg, int32_t frame) {
+    if (!cfg || (frame != 512 && frame != 1024)) return AEC_EINVAL;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->frame = frame;
+    cfg->partitions = 4;
+    cfg->algo = AEC_ALGO_NLMS;
+    cfg->mu = 0.5f;
+    cfg->delta = 1e-6f * (float)frame;
+    cfg->kalman_a = 0.999f;
+    cfg->kalman_lambda = 0.9f;
+    cfg->kalman_c0 = 1.0f;
+    cfg->kalman_eps = 1e-10f;
+    cfg->erle_skip_hops = 0;
+    cfg->variant = 0;
+    return AEC_OK;
+}
+
+extern "C" int64_t aec_num_frames(int64_t n_samples, int32_t frame) {
+    if (n_samples < 0 || frame <= 0 || (frame & 1)) return AEC_EINVAL;
+    const int64_t hop = frame / 2;
+    const int64_t padded = n_samples + 2 * (frame - hop);
+    if (padded < frame) return 0;
+    return (padded - frame) / hop + 1;
+}
+
+extern "C" int64_t aec_out_samples(int64_t n_samples, int32_t frame) {
+    const int64_t t = aec_num_frames(n_samples, frame);
+    if (t < 0) return t;
+    return t > 0 ? (t - 1) * (frame / 2) : 0;
+}
+
+extern "C" int64_t aec_launch_count(int reset) {
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1, device buffers
+// ------------------------------------------------------------------------------------------
+static int validate_cfg(const aec_cfg* cfg) {
+    if (!cfg) return AEC_EINVAL;
+    if (cfg->frame != 512 && cfg->frame != 1024) return AEC_EUNSUPPORTED;
+    if (cfg->partitions < 1) return AEC_EINVAL;
+    if (cfg->algo != AEC_ALGO_NLMS && cfg->algo != AEC_ALGO_KALMAN) return AEC_EINVAL;
+    if (cfg->erle_skip_hops < 0) return AEC_EINVAL;
+    return AEC_OK;
+}
+
+extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, float* echo_est, float* erle_db,
+                              const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride, int64_t out_stride,
+                              const aec_cfg* cfg, void* cuda_stream) {
+    int rc = validate_cfg(cfg);
+    if (rc != AEC_OK) return rc;
+    if (B < 0 || L < 0 || in_stride < L || out_stride < L) return AEC_EINVAL;
+    if (B == 0) return AEC_OK;
+    if (!far || !mic || !err) return AEC_EINVAL;
+    if (B > 0x7fffffffLL || L > 0x3fffffffLL) return AEC_EINVAL;
+    if (cfg->frame != 512) return AEC_EUNSUPPORTED;   // 1024-sample frames: see aec_stage1_1024.cu (next)
+    Tables tab;
+    rc = get_tables(&tab);
+    if (rc != AEC_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+
+    Stage1Params p{};
+    p.far = far;
+    p.mic = mic;
+    p.err = err;
+    p.echo = echo_est;
+    p.erle_db = erle_db;
+    p.n_samples = reinterpret_cast<const long long*>(n_samples);
+    p.B = B;
+    p.L = L;
+    p.in_stride = in_stride;
+    p.out_stride = out_stride;
+    p.mu = cfg->mu;
+    p.delta = cfg->delta;
+    p.ka = cfg->kalman_a;
+    p.ka2 = cfg->kalman_a * cfg->kalman_a;
+    p.kq = (float)(1.0 - (double)cfg->kalman_a * (double)cfg->kalman_a);
+    p.klam = cfg->kalman_lambda;
+    p.koml = 1.0f - cfg->kalman_lambda;
+    p.kc0 = cfg->kalman_c0;
+    p.keps = cfg->kalman_eps;
+    p.erle_skip_hops = cfg->erle_skip_hops;
+    auto aligned = [](const void* ptr, size_t a) { return (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) == 0; };
+    p.use_tma = (aligned(far, 16) && aligned(mic, 16) && (in_stride % 4) == 0) ? 1 : 0;
+    p.vec_out = (aligned(err, 8) && (!echo_est || aligned(echo_est, 8)) && (out_stride % 2) == 0) ? 1 : 0;
+    p.tw256 = tab.tw256;
+    p.tw512 = tab.tw512;
+    p.win_a = tab.win_a;
+    p.win_s = tab.win_s;
+
+    const int P = cfg->partitions;
+    const bool echo = echo_est != nullptr;
+    int nw = 0, minb = 0;
+    if (cfg->variant > 0) {
+        nw = cfg->variant / 100;
+        minb = cfg->variant % 100;
+    } else {
+        nw = (P <= 4) ? 2 : 4;
+    }
+    cudaError_t e;
+    switch (nw) {
+        case 1: e = launch_stage1_nw1(P, cfg->algo, echo, minb, p, s); break;
+        case 2: e = launch_stage1_nw2(P, cfg->algo, echo, minb, p, s); break;
+        case 4: e = launch_stage1_nw4(P, cfg->algo, echo, minb, p, s); break;
+        default: return AEC_EUNSUPPORTED;
+    }
+    if (e == cudaErrorInvalidValue) {
+        (void)cudaGetLastError();
+        return AEC_EUNSUPPORTED;
+    }
+    if (e != cudaSuccess) {
+        set_cuda_error(e, "stage1 kernel launch");
+        return AEC_ECUDA;
+    }
+    count_launch();
+    return AEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1, host buffers: double-buffered H2D -> kernel -> D2H pipeline
+// ------------------------------------------------------------------------------------------
+struct aec_host_ctx {
+    int device = 0;
+    int64_t slice = 0;       // utterances per slice
+    int64_t max_samples = 0;
+    int64_t stride = 0;      // device row stride (multiple of 4 floats)
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    float* d_far[2] = {nullptr, nullptr};
+    float* d_mic[2] = {nullptr, nullptr};
+    float* d_err[2] = {nullptr, nullptr};
+    float* d_echo[2] = {nullptr, nullptr};
+    float* d_erle[2] = {nullptr, nullptr};
+    long long* d_n[2] = {nullptr, nullptr};
+};
+
+extern "C" int aec_host_ctx_destroy(aec_host_ctx* ctx) {
+    if (!ctx) return AEC_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stream[i]) cudaStreamSynchronize(ctx->stream[i]);
+        cudaFree(ctx->d_far[i]);
+        cudaFree(ctx->d_mic[i]);
+        cudaFree(ctx->d_err[i]);
+        cudaFree(ctx->d_echo[i]);
+        cudaFree(ctx->d_erle[i]);
+        cudaFree(ctx->d_n[i]);
+        if (ctx->stream[i]) cudaStreamDestroy(ctx->stream[i]);
+    }
+    delete ctx;
+    return AEC_OK;
+}
+
+extern "C" int aec_host_ctx_create(aec_host_ctx** out, int64_t slice_utterances, int64_t max_samples) {
+    if (!out || slice_utterances <= 0 || max_samples <= 0) return AEC_EINVAL;
+    aec_host_ctx* ctx = new (std::nothrow) aec_host_ctx();
+    if (!ctx) return AEC_ENOMEM;
+    ctx->slice = slice_utterances;
+    ctx->max_samples = max_samples;
+    ctx->stride = (max_samples + 3) / 4 * 4;
+    cudaError_t e = cudaGetDevice(&ctx->device);
+    const size_t sig = (size_t)ctx->slice * (size_t)ctx->stride * sizeof(float);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->d_far[i], sig);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->d_mic[i], sig);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->d_err[i], sig);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->d_echo[i], sig);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->d_erle[i], (size_t)ctx->slice * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->d_n[i], (size_t)ctx->slice * sizeof(long long));
+    }
+    if (e != cudaSuccess) {
+        set_cuda_error(e, "aec_host_ctx_create");
+        aec_host_ctx_destroy(ctx);
+        return e == cudaErrorMemoryAllocation ? AEC_ENOMEM : AEC_ECUDA;
+    }
+    *out = ctx;
+    return AEC_OK;
+}
+
+extern "C" int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const float* mic, float* err, float* echo_est,
+                                   float* erle_db, const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride,
+                                   int64_t out_stride, const aec_cfg* cfg) {
+    if (!ctx) return AEC_EINVAL;
+    int rc = validate_cfg(cfg);
+    if (rc != AEC_OK) return rc;
+    if (B < 0 || L < 0 || L > ctx->max_samples || in_stride < L || out_stride < L) return AEC_EINVAL;
+    if (B == 0) return AEC_OK;
+    if (!far || !mic || !err) return AEC_EINVAL;
+    const size_t row = (size_t)L * sizeof(float);
+    const size_t dpitch = (size_t)ctx->stride * sizeof(float);
+    int first_rc = AEC_OK;
+    for (int64_t off = 0, it = 0; off < B; off += ctx->slice, ++it) {
+        const int k = (int)(it & 1);
+        const int64_t nb = (B - off < ctx->slice) ? (B - off) : ctx->slice;
+        cudaStream_t s = ctx->stream[k];
+        // the slot's previous slice has drained when its stream has (copies were enqueued on it)
+        AEC_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_far[k], dpitch, far + off * in_stride, (size_t)in_stride * sizeof(float),
+                                         row, (size_t)nb, cudaMemcpyHostToDevice, s));
+        AEC_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_mic[k], dpitch, mic + off * in_stride, (size_t)in_stride * sizeof(float),
+                                         row, (size_t)nb, cudaMemcpyHostToDevice, s));
+        if (n_samples)
+            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n[k], n_samples + off, (size_t)nb * sizeof(int64_t),
+                                           cudaMemcpyHostToDevice, s));
+        rc = aec_stage1_run(ctx->d_far[k], ctx->d_mic[k], ctx->d_err[k], echo_est ? ctx->d_echo[k] : nullptr,
+                            erle_db ? ctx->d_erle[k] : nullptr,
+                            n_samples ? reinterpret_cast<const int64_t*>(ctx->d_n[k]) : nullptr, nb, L, ctx->stride,
+                            ctx->stride, cfg, s);
+        if (rc != AEC_OK) {
+            first_rc = rc;
+            break;
+        }
+        AEC_CUDA_CHECK(cudaMemcpy2DAsync(err + off * out_stride, (size_t)out_stride * sizeof(float), ctx->d_err[k], dpitch,
+                                         row, (size_t)nb, cudaMemcpyDeviceToHost, s));
+        if (echo_est)
+            AEC_CUDA_CHECK(cudaMemcpy2DAsync(echo_est + off * out_stride, (size_t)out_stride * sizeof(float),
+                                             ctx->d_echo[k], dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
+        if (erle_db)
+            AEC_CUDA_CHECK(cudaMemcpyAsync(erle_db + off, ctx->d_erle[k], (size_t)nb * sizeof(float),
+                                           cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 2; ++i) AEC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream[i]));
+    return first_rc;
+}
+
+extern "C" int aec_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return AEC_EINVAL;
+    AEC_CUDA_CHECK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return AEC_OK;
+}
+
+extern "C" int aec_host_free(void* ptr) {
+    if (!ptr) return AEC_OK;
+    AEC_CUDA_CHECK(cudaFreeHost(ptr));
+    return AEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 peak probe
+// ------------------------------------------------------------------------------------------
+extern "C" int aec_bench_fp32_peak(int iters, double* tflops, void* cuda_stream) {
+    if (iters <= 0 || !tflops) return AEC_EINVAL;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    int dev = 0, sms = 0;
+    AEC_CUDA_CHECK(cudaGetDevice(&dev));
+    AEC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* d = nullptr;
+    AEC_CUDA_CHECK(cudaMalloc(&d, 256));
+    cudaEvent_t a, b;
+    AEC_CUDA_CHECK(cudaEventCreate(&a));
+    AEC_CUDA_CHECK(cudaEventCreate(&b));
+    const int blocks = sms * 8;
+    ffma_peak_kernel<<<blocks, 256, 0, s>>>(d, iters / 4 + 1, 0.999f, 1e-3f);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        AEC_CUDA_CHECK(cudaEventRecord(a, s));
+        ffma_peak_kernel<<<blocks, 256, 0, s>>>(d, iters, 0.999f, 1e-3f);
+        AEC_CUDA_CHECK(cudaEventRecord(b, s));
+        AEC_CUDA_CHECK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        AEC_CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+        const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    count_launch(6);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    AEC_CUDA_CHECK(cudaGetLastError());
+    *tflops = best;
+    return AEC_OK;
+}

@@ -1,0 +1,36 @@
+// Shared host-side helpers of the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/aec_b200.h"
+
+namespace aec {
+
+// Constant tables living in device global memory (one copy per device / context).
+struct Tables {
+    const float2* tw256;   // [16][16]  exp(-2 pi i h q / 256) at [q*16 + h]
+    const float2* tw512;   // [129]     exp(-2 pi i k / 512)
+    const float2* win_a;   // [256]     0.5 * hann512[2m], 0.5 * hann512[2m+1]
+    const float2* win_s;   // [256]     hann512[n] / (512 (coff[n] + 1e-8))
+    const float2* win_r;   // [256]     hann512[n] / 512        (raw synthesis frame, for aec_istft)
+    const float* hann512;  // [512]
+};
+
+// Returns AEC_OK and the tables of the current device (lazily initialised, thread safe).
+int get_tables(Tables* out);
+
+void set_cuda_error(cudaError_t e, const char* where);
+void count_launch(int n = 1);
+
+#define AEC_CUDA_CHECK(expr)                          \
+    do {                                              \
+        cudaError_t _e = (expr);                      \
+        if (_e != cudaSuccess) {                      \
+            ::aec::set_cuda_error(_e, #expr);         \
+            return AEC_ECUDA;                         \
+        }                                             \
+    } while (0)
+
+}  // namespace aec

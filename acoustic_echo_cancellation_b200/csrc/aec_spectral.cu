@@ -1,0 +1,313 @@
+// Stand-alone spectral operators behind the reference's operator seams (frame = 512):
+//   aec_stft      <-> ConvSTFT.forward      Stage2_lhm/scripts/network/attention_ccrn.py:45-52
+//   aec_istft     <-> ConviSTFT.forward     Stage2_lhm/scripts/network/attention_ccrn.py:82-101
+//   aec_features  <-> Little_net.forward    Stage2_lhm/scripts/network/ERB.py:262-290
+// All three reuse the half-warp FFT-256 of the fused stage-1 kernel; a CTA works on a tile of
+// 16 frames so the reference's [B, 2K, T] (T innermost) layout is read / written in 64-byte
+// runs through a shared-memory transpose.
+#include "aec_common.cuh"
+#include "fft_warp.cuh"
+
+namespace aec {
+
+namespace {
+
+constexpr int kTT = 16;        // frames per CTA tile
+constexpr int kThreads = 128;  // 8 half-warps, 2 frames each
+constexpr int kK = 257;
+constexpr int kPitch = kTT + 1;
+
+__device__ __forceinline__ void unpack_pair_s(float2 fa, float2 fb, float2 w, float2& xk, float2& xm) {
+    const float2 a = make_float2(fa.x + fb.x, fa.y - fb.y);
+    const float2 d = make_float2(fa.y + fb.y, fb.x - fa.x);
+    const float2 t = cmul(w, d);
+    xk = make_float2(a.x + t.x, a.y + t.y);
+    xm = make_float2(a.x - t.x, t.y - a.y);
+}
+__device__ __forceinline__ void pack_pair_s(float2 ek, float2 em, float2 w, float2& gk, float2& gm) {
+    const float2 a = make_float2(ek.x + em.x, ek.y - em.y);
+    const float2 d = make_float2(ek.x - em.x, ek.y + em.y);
+    const float2 t = cmulc(d, w);
+    gk = make_float2(a.x - t.y, a.y + t.x);
+    gm = make_float2(a.x + t.y, t.x - a.y);
+}
+
+// Windowed analysis of frame t of one row into the half-warp's tile: tile[k] = Zc[k].
+// `shift` is subtracted from in-range samples only (the zero pad stays zero, as in the
+// reference where the shift precedes ConvSTFT's F.pad).
+__device__ __forceinline__ void analyse_frame(const float* __restrict__ x, long long L, long long t, float shift,
+                                              float2* tile, const Tables& tab, int h) {
+    float2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const long long s = (t - 1) * 256 + 2 * h + 32 * j;
+        const float2 w = __ldg(&tab.win_a[h + 16 * j]);
+        const float x0 = (s >= 0 && s < L) ? __ldg(x + s) - shift : 0.f;
+        const float x1 = (s + 1 >= 0 && s + 1 < L) ? __ldg(x + s + 1) - shift : 0.f;
+        v[j] = make_float2(x0 * w.x, x1 * w.y);
+    }
+    __syncwarp();
+    fft256_halfwarp<false>(v, tile, tab.tw256, h);
+#pragma unroll
+    for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------
+// STFT: x [B][in_stride] -> spec [B][514][T]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) stft512_kernel(const float* __restrict__ x, float* __restrict__ spec,
+                                                           long long L, long long in_stride, long long T, Tables tab) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* tiles = reinterpret_cast<float2*>(smem);                       // [8][256]
+    float* outt = reinterpret_cast<float*>(smem + 8 * 256 * sizeof(float2));  // [514][kPitch]
+    const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
+    const long long b = blockIdx.y, t0 = (long long)blockIdx.x * kTT;
+    const float* xb = x + b * in_stride;
+    float2* tile = tiles + hw * 256;
+    for (int i = 0; i < 2; ++i) {
+        const int tt = hw + 8 * i;
+        const long long t = t0 + tt;
+        {   // frames beyond T are analysed as zeros (loads predicated off) and never stored
+            analyse_frame(xb, t < T ? L : 0, t, 0.f, tile, tab, h);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = h + 16 * q;
+                float2 xk, xm;
+                unpack_pair_s(tile[k], tile[(256 - k) & 255], __ldg(&tab.tw512[k]), xk, xm);
+                outt[k * kPitch + tt] = xk.x;
+                outt[(kK + k) * kPitch + tt] = (k == 0) ? 0.f : xk.y;
+                outt[(256 - k) * kPitch + tt] = xm.x;
+                outt[(kK + 256 - k) * kPitch + tt] = (k == 0) ? 0.f : xm.y;
+            }
+            if (h == 0) {
+                float2 xk, xm;
+                unpack_pair_s(tile[128], tile[128], make_float2(0.f, -1.f), xk, xm);
+                outt[128 * kPitch + tt] = xk.x;
+                outt[(kK + 128) * kPitch + tt] = xk.y;
+            }
+        }
+    }
+    __syncthreads();
+    float* sb = spec + b * (2 * kK) * T;
+    for (int idx = tid; idx < 2 * kK * kTT; idx += kThreads) {
+        const int c = idx / kTT, tt = idx % kTT;
+        if (t0 + tt < T) sb[(long long)c * T + t0 + tt] = outt[c * kPitch + tt];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// iSTFT: spec [B][514][T] -> y [B][out_stride], (T-1)*256 samples per row.
+// CTA emits output hops [g0, g0+15): needs frames g0 .. g0+15 (16 frames).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) istft512_kernel(const float* __restrict__ spec, float* __restrict__ y,
+                                                            long long T, long long out_stride, Tables tab) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* tiles = reinterpret_cast<float2*>(smem);                        // [8][256]
+    float* inn = reinterpret_cast<float*>(smem + 8 * 256 * sizeof(float2));    // [514][kPitch], later frames [16][512]
+    const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
+    const long long b = blockIdx.y, g0 = (long long)blockIdx.x * (kTT - 1);   // first output hop == first frame
+    const float* sb = spec + b * (2 * kK) * T;
+    for (int idx = tid; idx < 2 * kK * kTT; idx += kThreads) {
+        const int c = idx / kTT, tt = idx % kTT;
+        inn[c * kPitch + tt] = (g0 + tt < T) ? __ldg(sb + (long long)c * T + g0 + tt) : 0.f;
+    }
+    __syncthreads();
+    float2* tile = tiles + hw * 256;
+    float2 u[2][16];
+    for (int i = 0; i < 2; ++i) {
+        const int tt = hw + 8 * i;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = h + 16 * q;
+            float2 ek = make_float2(inn[k * kPitch + tt], inn[(kK + k) * kPitch + tt]);
+            float2 em = make_float2(inn[(256 - k) * kPitch + tt], inn[(kK + 256 - k) * kPitch + tt]);
+            if (k == 0) {   // imaginary parts of DC / Nyquist have zero rows in the synthesis kernel
+                ek.y = 0.f;
+                em.y = 0.f;
+            }
+            float2 gk, gm;
+            pack_pair_s(ek, em, __ldg(&tab.tw512[k]), gk, gm);
+            tile[k] = gk;
+            tile[(256 - k) & 255] = gm;
+        }
+        if (h == 0) {
+            const float2 e = make_float2(inn[128 * kPitch + tt], inn[(kK + 128) * kPitch + tt]);
+            float2 gk, gm;
+            pack_pair_s(e, e, make_float2(0.f, -1.f), gk, gm);
+            tile[128] = gk;
+        }
+        __syncwarp();
+        float2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = tile[h + 16 * j];
+        __syncwarp();
+        fft256_halfwarp<true>(v, tile, tab.tw256, h);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const int r = fft16_index(p);
+            const float2 w = __ldg(&tab.win_s[h + 16 * r]);
+            u[i][r] = make_float2(v[p].x * w.x, v[p].y * w.y);
+        }
+        __syncwarp();
+    }
+    __syncthreads();   // spectra consumed: reuse `inn` for the windowed frames
+    float2* fr = reinterpret_cast<float2*>(inn);   // [16][256] float2 (sample pairs)
+    for (int i = 0; i < 2; ++i) {
+        const int tt = hw + 8 * i;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) fr[tt * 256 + h + 16 * r] = u[i][r];
+    }
+    __syncthreads();
+    float* yb = y + b * out_stride;
+    // output hop g (samples g*256 ..) = second half of frame g + first half of frame g+1
+    for (int idx = tid; idx < (kTT - 1) * 128; idx += kThreads) {
+        const int tt = idx / 128, m = idx % 128;
+        const long long g = g0 + tt;
+        if (g + 1 <= T - 1) {
+            const float2 a = fr[tt * 256 + 128 + m];
+            const float2 c = fr[(tt + 1) * 256 + m];
+            yb[g * 256 + 2 * m] = a.x + c.x;
+            yb[g * 256 + 2 * m + 1] = a.y + c.y;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Stage-2 feature front end: feat [B][T][2*bands]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) features512_kernel(const float* __restrict__ mic,
+                                                               const float* __restrict__ ref,
+                                                               const float* __restrict__ erb, float* __restrict__ feat,
+                                                               long long L, long long in_stride, long long T, int bands,
+                                                               float shift_mic, float shift_ref, Tables tab) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int kMP = 260;   // magnitude row pitch
+    float2* tiles = reinterpret_cast<float2*>(smem);                             // [8][256]
+    float* mag = reinterpret_cast<float*>(smem + 8 * 256 * sizeof(float2));         // [2][kTT][kMP]
+    float* erbs = mag + 2 * kTT * kMP;                                           // [257][bands]
+    const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
+    const long long b = blockIdx.y, t0 = (long long)blockIdx.x * kTT;
+    for (int idx = tid; idx < kK * bands; idx += kThreads) erbs[idx] = __ldg(erb + idx);
+    float2* tile = tiles + hw * 256;
+    for (int sig = 0; sig < 2; ++sig) {
+        const float* xb = (sig == 0 ? mic : ref) + b * in_stride;
+        const float shift = sig == 0 ? shift_mic : shift_ref;
+        for (int i = 0; i < 2; ++i) {
+            const int tt = hw + 8 * i;
+            const long long t = t0 + tt;
+            float* mrow = mag + (sig * kTT + tt) * kMP;
+            {
+                analyse_frame(xb, t < T ? L : 0, t, shift, tile, tab, h);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = h + 16 * q;
+                    float2 xk, xm;
+                    unpack_pair_s(tile[k], tile[(256 - k) & 255], __ldg(&tab.tw512[k]), xk, xm);
+                    if (k == 0) {
+                        xk.y = 0.f;
+                        xm.y = 0.f;
+                    }
+                    mrow[k] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));        // ERB.py:277-278
+                    mrow[256 - k] = sqrtf(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
+                }
+                if (h == 0) {
+                    float2 xk, xm;
+                    unpack_pair_s(tile[128], tile[128], make_float2(0.f, -1.f), xk, xm);
+                    mrow[128] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float* fb = feat + b * T * (2 * bands);
+    for (int idx = tid; idx < kTT * bands; idx += kThreads) {
+        const int tt = idx / bands, band = idx % bands;
+        if (t0 + tt >= T) continue;
+        const float* m0 = mag + (0 * kTT + tt) * kMP;
+        const float* m1 = mag + (1 * kTT + tt) * kMP;
+        float am = 0.f, ar = 0.f;
+        for (int k = 0; k < kK; ++k) {
+            const float e = erbs[k * bands + band];
+            am = fmaf(m0[k], e, am);                                                    // ERB.py:282
+            ar = fmaf(m1[k], e, ar);                                                    // ERB.py:283
+        }
+        float* dst = fb + (t0 + tt) * (2 * bands);
+        dst[band] = am;
+        dst[bands + band] = fabsf(am - ar);                                             // ERB.py:287-290
+    }
+}
+
+template <typename K>
+int set_smem(K kern, size_t bytes) {
+    AEC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return AEC_OK;
+}
+
+}  // namespace
+}  // namespace aec
+
+using namespace aec;
+
+extern "C" int aec_stft(const float* x, float* spec, int64_t B, int64_t L, int64_t in_stride, int32_t frame,
+                        void* cuda_stream) {
+    if (B < 0 || L < 0 || in_stride < L) return AEC_EINVAL;
+    if (frame != 512) return frame == 1024 ? AEC_EUNSUPPORTED : AEC_EINVAL;
+    if (B == 0) return AEC_OK;
+    if (!x || !spec || B > 65535) return AEC_EINVAL;
+    Tables tab;
+    int rc = get_tables(&tab);
+    if (rc != AEC_OK) return rc;
+    const long long T = aec_num_frames(L, frame);
+    const size_t smem = 8 * 256 * sizeof(float2) + (size_t)2 * kK * kPitch * sizeof(float);
+    rc = set_smem(stft512_kernel, smem);
+    if (rc != AEC_OK) return rc;
+    dim3 grid((unsigned)((T + kTT - 1) / kTT), (unsigned)B);
+    stft512_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(x, spec, L, in_stride, T, tab);
+    AEC_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return AEC_OK;
+}
+
+extern "C" int aec_istft(const float* spec, float* y, int64_t B, int64_t T, int64_t out_stride, int32_t frame,
+                         void* cuda_stream) {
+    if (B < 0 || T < 0) return AEC_EINVAL;
+    if (frame != 512) return frame == 1024 ? AEC_EUNSUPPORTED : AEC_EINVAL;
+    if (T >= 1 && out_stride < (T - 1) * 256) return AEC_EINVAL;
+    if (B == 0 || T <= 1) return AEC_OK;
+    if (!spec || !y || B > 65535) return AEC_EINVAL;
+    Tables tab;
+    int rc = get_tables(&tab);
+    if (rc != AEC_OK) return rc;
+    const size_t smem = 8 * 256 * sizeof(float2) + (size_t)2 * kK * kPitch * sizeof(float);
+    rc = set_smem(istft512_kernel, smem);
+    if (rc != AEC_OK) return rc;
+    const long long hops = T - 1;
+    dim3 grid((unsigned)((hops + kTT - 2) / (kTT - 1)), (unsigned)B);
+    istft512_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(spec, y, T, out_stride, tab);
+    AEC_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return AEC_OK;
+}
+
+extern "C" int aec_features(const float* mic, const float* ref, const float* erb, float* feat, int64_t B, int64_t L,
+                            int64_t in_stride, int32_t frame, int32_t bands, float shift_mic, float shift_ref,
+                            void* cuda_stream) {
+    if (B < 0 || L < 0 || in_stride < L || bands < 1 || bands > 64) return AEC_EINVAL;
+    if (frame != 512) return frame == 1024 ? AEC_EUNSUPPORTED : AEC_EINVAL;
+    if (B == 0) return AEC_OK;
+    if (!mic || !ref || !erb || !feat || B > 65535) return AEC_EINVAL;
+    Tables tab;
+    int rc = get_tables(&tab);
+    if (rc != AEC_OK) return rc;
+    const long long T = aec_num_frames(L, frame);
+    const size_t smem = 8 * 256 * sizeof(float2) + (size_t)2 * kTT * 260 * sizeof(float) + (size_t)kK * bands * sizeof(float);
+    rc = set_smem(features512_kernel, smem);
+    if (rc != AEC_OK) return rc;
+    dim3 grid((unsigned)((T + kTT - 1) / kTT), (unsigned)B);
+    features512_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
+        mic, ref, erb, feat, L, in_stride, T, bands, shift_mic, shift_ref, tab);
+    AEC_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return AEC_OK;
+}

@@ -1,0 +1,123 @@
+// Warp-level FFT building blocks for the stage-1 AEC kernels (sm_100a).
+//
+// A real frame of N = 512 samples is transformed through ONE 256-point complex FFT
+// (even samples -> real lane, odd samples -> imaginary lane) executed by a HALF-WARP:
+// 16 lanes x 16 complex points in registers, two radix-16 passes, one exchange through
+// a 2 KB XOR-swizzled shared-memory tile (no padding, no bank conflicts).  A warp
+// therefore transforms two real frames at once (far-end + microphone on analysis,
+// two consecutive frames on synthesis).  The split into the real spectrum
+// X[0..256] (and the inverse packing) is done by the per-bin filter threads.
+//
+// Conventions follow the reference STFT operators (np.fft.rfft sign, periodic Hann):
+//   Stage2_lhm/scripts/network/attention_ccrn.py:8-25   (analysis / synthesis kernels)
+#pragma once
+#include <cuda_runtime.h>
+
+namespace aec {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(-a.y, b.y, a.x * b.x), fmaf(a.y, b.x, a.x * b.y));
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+    return make_float2(fmaf(a.y, b.y, a.x * b.x), fmaf(a.y, b.x, -(a.x * b.y)));
+}
+// acc + a*b
+__device__ __forceinline__ float2 cfma(float2 a, float2 b, float2 acc) {
+    return make_float2(fmaf(-a.y, b.y, fmaf(a.x, b.x, acc.x)), fmaf(a.y, b.x, fmaf(a.x, b.y, acc.y)));
+}
+// acc + conj(a)*b
+__device__ __forceinline__ float2 cfmac(float2 a, float2 b, float2 acc) {
+    return make_float2(fmaf(a.y, b.y, fmaf(a.x, b.x, acc.x)), fmaf(-a.y, b.x, fmaf(a.x, b.y, acc.y)));
+}
+
+// 4-point DFT in place.  INV=false: e^{-2 pi i jq/4};  INV=true: e^{+2 pi i jq/4}.
+template <bool INV>
+__device__ __forceinline__ void radix4(float2& a, float2& b, float2& c, float2& d) {
+    const float2 s0 = cadd(a, c), d0 = csub(a, c);
+    const float2 s1 = cadd(b, d), d1 = csub(b, d);
+    // forward: -i*d1 = (d1.y, -d1.x);  inverse: +i*d1 = (-d1.y, d1.x)
+    const float2 r = INV ? make_float2(-d1.y, d1.x) : make_float2(d1.y, -d1.x);
+    a = cadd(s0, s1);
+    c = csub(s0, s1);
+    b = cadd(d0, r);
+    d = csub(d0, r);
+}
+
+// multiply by w16^m (forward) or its conjugate (inverse), m a compile-time constant
+template <int M, bool INV>
+__device__ __forceinline__ float2 mul_w16(float2 v) {
+    constexpr float C1 = 0.92387953251128673848f;   // cos(pi/8)
+    constexpr float S1 = 0.38268343236508978178f;   // sin(pi/8)
+    constexpr float R2 = 0.70710678118654752440f;   // sqrt(1/2)
+    // forward twiddle w = (cr, ci) with ci <= 0 ; inverse uses (cr, -ci)
+    if constexpr (M == 0) return v;
+    if constexpr (M == 4) return INV ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
+    if constexpr (M == 2) {
+        return INV ? make_float2(R2 * (v.x - v.y), R2 * (v.x + v.y))
+                   : make_float2(R2 * (v.x + v.y), R2 * (v.y - v.x));
+    }
+    if constexpr (M == 6) {
+        return INV ? make_float2(-R2 * (v.x + v.y), R2 * (v.x - v.y))
+                   : make_float2(R2 * (v.y - v.x), -R2 * (v.x + v.y));
+    }
+    constexpr float cr = (M == 1) ? C1 : (M == 3) ? S1 : /*M == 9*/ -C1;
+    constexpr float cif = (M == 1) ? -S1 : (M == 3) ? -C1 : /*M == 9*/ S1;
+    constexpr float ci = INV ? -cif : cif;
+    return make_float2(fmaf(-v.y, ci, v.x * cr), fmaf(v.y, cr, v.x * ci));
+}
+
+// 16-point DFT in place on registers.  Input v[j], j = 0..15.  On return register
+// position p holds output index q = fft16_index(p) (digit reversal, compile time).
+__host__ __device__ constexpr int fft16_index(int p) { return (p >> 2) + 4 * (p & 3); }
+
+template <bool INV>
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+#pragma unroll
+    for (int j2 = 0; j2 < 4; ++j2) radix4<INV>(v[j2], v[4 + j2], v[8 + j2], v[12 + j2]);
+    // position 4*q1 + j2 holds t[j2][q1]; twiddle by w16^(j2*q1)
+    v[5] = mul_w16<1, INV>(v[5]);
+    v[6] = mul_w16<2, INV>(v[6]);
+    v[7] = mul_w16<3, INV>(v[7]);
+    v[9] = mul_w16<2, INV>(v[9]);
+    v[10] = mul_w16<4, INV>(v[10]);
+    v[11] = mul_w16<6, INV>(v[11]);
+    v[13] = mul_w16<3, INV>(v[13]);
+    v[14] = mul_w16<6, INV>(v[14]);
+    v[15] = mul_w16<9, INV>(v[15]);
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) radix4<INV>(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
+}
+
+// Half-warp 256-point complex FFT.
+//   h      : lane & 15
+//   v[j]   : on entry  z[h + 16 j]                 (j = 0..15)
+//            on return Z[h + 16 fft16_index(p)] in register position p
+//   tile   : 256 float2 of shared memory private to this half-warp (used as the
+//            exchange buffer; contents destroyed).  Caller guarantees every lane of the
+//            warp has finished reading whatever lived in `tile` (a __syncwarp precedes).
+//   tw     : global/L1 table tw[q*16 + h] = exp(-2 pi i h q / 256)
+template <bool INV>
+__device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2* tile, const float2* __restrict__ tw,
+                                                int h) {
+    fft16<INV>(v);
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+        const int q = fft16_index(p);
+        float2 x = v[p];
+        if (q != 0) {
+            const float2 w = __ldg(&tw[q * 16 + h]);
+            x = INV ? cmulc(x, w) : cmul(x, w);
+        }
+        tile[h * 16 + (q ^ h)] = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < 16; ++l) v[l] = tile[l * 16 + (h ^ l)];
+    __syncwarp();
+    fft16<INV>(v);
+}
+
+}  // namespace aec

@@ -1,0 +1,458 @@
+// Stage-1 linear echo canceller: fused STFT -> partitioned FDAF -> iSTFT, one persistent
+// CTA per utterance, N = 512 (16 kHz live configuration of the reference:
+// Stage2_lhm/scripts/configs.py:1-8, network/ERB.py:223-224).
+//
+// The reference has no stage-1 filter; the STFT/iSTFT conventions follow its operators
+// (Stage2_lhm/scripts/network/attention_ccrn.py:45-52 and :82-101) and the recurrence is the
+// builder-authored one frozen in DESIGN.md and restated by oracle/aec_oracle.py.
+//
+// Per chunk of F = 2*NW frames (NW = warps per CTA):
+//   phase A  analysis : each warp transforms one frame at a time; lanes 0-15 far-end, 16-31
+//                       microphone (two half-warp FFT-256 of the even/odd-packed real frame).
+//   phase B  filter   : every thread owns mirrored bin pairs (k, 256-k); unpacks X,Y from the
+//                       half-size spectra, runs the NLMS / Kalman recurrence with the filter
+//                       taps, far-end history and covariances resident in REGISTERS for the
+//                       whole utterance, and packs E (and Yhat) for the inverse transform
+//                       in place.
+//   phase C  synthesis: each warp inverts two consecutive frames (one per half-warp), applies
+//                       the synthesis window / overlap-add normaliser, adds the in-warp
+//                       overlap with one shuffle and the cross-warp overlap through 1 KB
+//                       tails in shared memory, and streams the error signal to HBM.
+// Far-end / microphone hops are staged HBM -> shared memory by the bulk-copy engine (TMA,
+// cp.async.bulk + mbarrier) one chunk ahead of the analysis phase; spectra never touch HBM.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "fft_warp.cuh"
+
+namespace aec {
+
+enum { kAlgoNlms = 0, kAlgoKalman = 1 };
+
+struct Stage1Params {
+    const float* far;
+    const float* mic;
+    float* err;
+    float* echo;       // nullable (only read by ECHO instantiations)
+    float* erle_db;    // nullable
+    const long long* n_samples;  // nullable -> every utterance has L samples
+    long long B, L, in_stride, out_stride;
+    float mu, delta;                         // NLMS
+    float ka, ka2, kq, klam, koml, kc0, keps;  // Kalman: A, A^2, 1-A^2, lambda, 1-lambda, c0, eps
+    int erle_skip_hops;
+    int use_tma;      // inputs 16-byte aligned per hop -> bulk copies
+    int vec_out;      // outputs 8-byte aligned -> float2 stores
+    const float2* tw256;   // [16][16]  exp(-2 pi i h q / 256) at [q*16 + h]
+    const float2* tw512;   // [129]     exp(-2 pi i k / 512)
+    const float2* win_a;   // [256]     0.5 * hann[2m], 0.5 * hann[2m+1]
+    const float2* win_s;   // [256]     hann[n] / (512 * (coff[n] + 1e-8)), n = 2m, 2m+1
+};
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA) wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "AEC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra AEC_DONE;\n"
+        "bra AEC_WAIT;\n"
+        "AEC_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void st_stream_f2(float* p, float2 v) {
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream_f1(float* p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// per-bin recurrence state, resident in registers
+// ------------------------------------------------------------------------------------------
+template <int P, int ALGO>
+struct BinState {
+    float2 W[P];   // filter taps
+    float2 X[P];   // X[p] = far-end spectrum p hops ago (X[0] = current after the shift)
+    float C[ALGO == kAlgoKalman ? P : 1];
+    float psi;
+    __device__ __forceinline__ void init(float c0) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            W[p] = make_float2(0.f, 0.f);
+            X[p] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int p = 0; p < (ALGO == kAlgoKalman ? P : 1); ++p) C[p] = c0;
+        psi = 0.f;
+    }
+};
+
+// One frame of the recurrence for one bin.  Operation order mirrors oracle/aec_oracle.py
+// (fdaf_nlms / fdaf_kalman).
+template <int P, int ALGO>
+__device__ __forceinline__ void bin_step(BinState<P, ALGO>& s, const float2 Xn, const float2 Y,
+                                         const Stage1Params& prm, float2& E, float2& Yh) {
+#pragma unroll
+    for (int p = P - 1; p > 0; --p) s.X[p] = s.X[p - 1];
+    s.X[0] = Xn;
+    float2 yh = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < P; ++p) yh = cfma(s.W[p], s.X[p], yh);
+    const float2 e = csub(Y, yh);
+    if constexpr (ALGO == kAlgoNlms) {
+        float pw = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) pw = fmaf(s.X[p].x, s.X[p].x, fmaf(s.X[p].y, s.X[p].y, pw));
+        const float g = __fdividef(prm.mu, pw + prm.delta);
+        const float2 ge = make_float2(g * e.x, g * e.y);
+#pragma unroll
+        for (int p = 0; p < P; ++p) s.W[p] = cfmac(s.X[p], ge, s.W[p]);
+    } else {
+        const float e2 = fmaf(e.x, e.x, e.y * e.y);
+        s.psi = fmaf(prm.klam, s.psi, prm.koml * e2);
+        float cx2[P];
+        float d = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float x2 = fmaf(s.X[p].x, s.X[p].x, s.X[p].y * s.X[p].y);
+            cx2[p] = s.C[p] * x2;
+            d += cx2[p];
+        }
+        d = d + s.psi + prm.keps;
+        const float rd = __frcp_rn(d);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float gs = s.C[p] * rd;
+            const float2 g = make_float2(gs * s.X[p].x, -gs * s.X[p].y);   // C conj(X) / D
+            float2 w = cfma(g, e, s.W[p]);
+            w = make_float2(prm.ka * w.x, prm.ka * w.y);
+            s.W[p] = w;
+            const float w2 = fmaf(w.x, w.x, w.y * w.y);
+            s.C[p] = fmaf(prm.ka2 * (1.f - cx2[p] * rd), s.C[p], prm.kq * w2);
+        }
+    }
+    E = e;
+    Yh = yh;
+}
+
+// half-size spectra -> the two real-signal bins of the mirrored pair (k, 256-k).
+// fa = Zc[k], fb = Zc[256-k], w = exp(-2 pi i k/512).  The analysis window carries the 1/2.
+__device__ __forceinline__ void unpack_pair(float2 fa, float2 fb, float2 w, float2& xk, float2& xm) {
+    const float2 a = make_float2(fa.x + fb.x, fa.y - fb.y);          // Zc[k] + conj Zc[256-k]
+    const float2 d = make_float2(fa.y + fb.y, fb.x - fa.x);          // (Zc[k] - conj Zc[256-k]) / i
+    const float2 t = cmul(w, d);
+    xk = make_float2(a.x + t.x, a.y + t.y);
+    xm = make_float2(a.x - t.x, t.y - a.y);                          // conj(a - t)
+}
+// two real-signal bins (k, 256-k) -> half-size inverse spectrum entries G[k], G[256-k]
+// (scale 1/512 lives in the synthesis table).
+__device__ __forceinline__ void pack_pair(float2 ek, float2 em, float2 w, float2& gk, float2& gm) {
+    const float2 a = make_float2(ek.x + em.x, ek.y - em.y);          // E[k] + conj E[256-k]
+    const float2 d = make_float2(ek.x - em.x, ek.y + em.y);          // E[k] - conj E[256-k]
+    const float2 t = cmulc(d, w);                                    // d * conj(w)
+    gk = make_float2(a.x - t.y, a.y + t.x);
+    gm = make_float2(a.x + t.y, t.x - a.y);
+}
+
+template <int NW>
+struct Stage1Smem {
+    static constexpr int F = 2 * NW;        // frames per chunk
+    static constexpr int R = F + 1;         // staging ring, hops per signal
+    static constexpr size_t zbuf_bytes = size_t(F) * 2 * 256 * sizeof(float2);
+    static constexpr size_t stage_bytes = size_t(2) * R * 256 * sizeof(float);
+    __host__ __device__ static constexpr size_t tails_bytes(bool echo) { return size_t(NW + 1) * 128 * sizeof(float2) * (echo ? 2 : 1); }
+    __host__ __device__ static constexpr size_t total(bool echo) { return zbuf_bytes + stage_bytes + tails_bytes(echo) + 64; }
+};
+
+template <int NW, int P, int ALGO, bool ECHO, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) stage1_n512_kernel(const Stage1Params prm) {
+    using SM = Stage1Smem<NW>;
+    constexpr int F = SM::F, R = SM::R, NT = NW * 32;
+    constexpr int PPT = 128 / NT;            // mirrored pairs per thread
+    static_assert(PPT >= 1, "at most 4 warps per utterance");
+    constexpr int NSIG = ECHO ? 2 : 1;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* zbuf = reinterpret_cast<float2*>(smem_raw);                               // [F][2][256]
+    float* stage = reinterpret_cast<float*>(smem_raw + SM::zbuf_bytes);               // [2][R][256]
+    float2* tails = reinterpret_cast<float2*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes);  // [NSIG][NW+1][128]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes +
+                                                 SM::tails_bytes(ECHO));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = lane >> 4, h = lane & 15;
+    const long long b = blockIdx.x;
+
+    long long n_ll = prm.n_samples ? prm.n_samples[b] : prm.L;
+    n_ll = n_ll < 0 ? 0 : (n_ll > prm.L ? prm.L : n_ll);
+    const int n = static_cast<int>(n_ll);
+    const int T = n / 256 + 1;               // frames (attention_ccrn.py:48-49 with N = 2H)
+    const int n_chunks = (T + F - 1) / F;
+    const float* far_b = prm.far + b * prm.in_stride;
+    const float* mic_b = prm.mic + b * prm.in_stride;
+    float* out_b[2] = {prm.err + b * prm.out_stride, ECHO ? prm.echo + b * prm.out_stride : nullptr};
+
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // hops (padded-signal blocks) [b0, b1] -> staging ring.  Block beta holds samples
+    // [(beta-1)*256, beta*256); block 0 is the reference's left zero pad.
+    auto produce = [&](int b0, int b1) {
+        if (b1 > T) b1 = T;
+        if (lane == 0) {
+            int nt = 0;
+            for (int beta = b0; beta <= b1; ++beta) nt += (prm.use_tma && beta >= 1 && beta * 256 <= n) ? 1 : 0;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(mbar, static_cast<uint32_t>(nt) * 2048u);
+            for (int beta = b0; beta <= b1; ++beta) {
+                if (prm.use_tma && beta >= 1 && beta * 256 <= n) {
+                    const int slot = beta % R;
+                    tma_load_1d(stage + (0 * R + slot) * 256, far_b + (beta - 1) * 256, 1024u, mbar);
+                    tma_load_1d(stage + (1 * R + slot) * 256, mic_b + (beta - 1) * 256, 1024u, mbar);
+                }
+            }
+        }
+        for (int beta = b0; beta <= b1; ++beta) {
+            if (!(prm.use_tma && beta >= 1 && beta * 256 <= n)) {
+                const int slot = beta % R;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int o = lane + 32 * i;
+                    const int idx = (beta - 1) * 256 + o;
+                    const bool ok = beta >= 1 && idx < n;
+                    stage[(0 * R + slot) * 256 + o] = ok ? __ldg(far_b + idx) : 0.f;
+                    stage[(1 * R + slot) * 256 + o] = ok ? __ldg(mic_b + idx) : 0.f;
+                }
+            }
+        }
+    };
+
+    if (warp == 0) produce(0, F);
+
+    // ---- persistent recurrence state -------------------------------------------------------
+    BinState<P, ALGO> st[2 * PPT];
+    BinState<P, ALGO> st_mid;               // bin 128, owned by the last thread
+    float2 wk[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        st[2 * i].init(prm.kc0);
+        st[2 * i + 1].init(prm.kc0);
+        wk[i] = __ldg(&prm.tw512[tid + i * NT]);
+    }
+    st_mid.init(prm.kc0);
+    const float2 w_mid = make_float2(0.f, -1.f);
+
+    float acc_mic = 0.f, acc_err = 0.f;      // ERLE energies (mic: lanes 16-31, err: lanes 0-15)
+    const bool want_erle = prm.erle_db != nullptr;
+
+    for (int c = 0; c < n_chunks; ++c) {
+        const int t0 = c * F;
+        __syncthreads();                     // manual-path staging stores of the producer visible
+        mbar_wait(mbar, static_cast<uint32_t>(c & 1));
+
+        // ================= phase A : analysis =================
+#pragma unroll 1
+        for (int i = 0; i < 2; ++i) {
+            const int tl = warp + NW * i;
+            const int t = t0 + tl;
+            if (t < T) {
+                const float* s0 = stage + (half * R + (t % R)) * 256 + 2 * h;
+                const float* s1 = stage + (half * R + ((t + 1) % R)) * 256 + 2 * h;
+                float2 v[16];
+                float e_acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float2 x = *reinterpret_cast<const float2*>((j < 8 ? s0 : s1) + 32 * (j & 7));
+                    const float2 w = __ldg(&prm.win_a[h + 16 * j]);
+                    v[j] = make_float2(x.x * w.x, x.y * w.y);
+                    if (j >= 8) e_acc = fmaf(x.x, x.x, fmaf(x.y, x.y, e_acc));
+                }
+                // second half of frame t is output hop t (block t+1): inside the ERLE span?
+                if (want_erle && half == 1 && t + 1 <= T - 1 && t >= prm.erle_skip_hops) acc_mic += e_acc;
+                float2* tile = zbuf + (tl * 2 + half) * 256;
+                fft256_halfwarp<false>(v, tile, prm.tw256, h);
+#pragma unroll
+                for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
+            }
+        }
+        __syncthreads();
+
+        // stage the next chunk's hops while the filter and synthesis phases run
+        if (warp == 0 && c + 1 < n_chunks) produce(t0 + F + 1, t0 + 2 * F);
+
+        // ================= phase B : per-bin recurrence =================
+#pragma unroll
+        for (int tl = 0; tl < F; ++tl) {
+            if (t0 + tl < T) {
+                float2* zf = zbuf + (tl * 2 + 0) * 256;
+                float2* zm = zbuf + (tl * 2 + 1) * 256;
+#pragma unroll
+                for (int i = 0; i < PPT; ++i) {
+                    const int k = tid + i * NT;
+                    const int km = (256 - k) & 255;
+                    float2 xk, xm, yk, ym, ek, em, hk, hm, gk, gm;
+                    unpack_pair(zf[k], zf[km], wk[i], xk, xm);
+                    unpack_pair(zm[k], zm[km], wk[i], yk, ym);
+                    bin_step<P, ALGO>(st[2 * i], xk, yk, prm, ek, hk);
+                    bin_step<P, ALGO>(st[2 * i + 1], xm, ym, prm, em, hm);
+                    if (k == 0) {            // DC / Nyquist: imaginary parts do not contribute
+                        ek.y = 0.f; em.y = 0.f; hk.y = 0.f; hm.y = 0.f;
+                    }
+                    pack_pair(ek, em, wk[i], gk, gm);
+                    zf[k] = gk;
+                    zf[km] = gm;
+                    if constexpr (ECHO) {
+                        pack_pair(hk, hm, wk[i], gk, gm);
+                        zm[k] = gk;
+                        zm[km] = gm;
+                    }
+                }
+                if (tid == NT - 1) {         // self-mirrored bin 128
+                    float2 xk, xm, yk, ym, ek, hk, gk, gm;
+                    const float2 fa = zf[128], ma = zm[128];
+                    unpack_pair(fa, fa, w_mid, xk, xm);
+                    unpack_pair(ma, ma, w_mid, yk, ym);
+                    bin_step<P, ALGO>(st_mid, xk, yk, prm, ek, hk);
+                    pack_pair(ek, ek, w_mid, gk, gm);
+                    zf[128] = gk;
+                    if constexpr (ECHO) {
+                        pack_pair(hk, hk, w_mid, gk, gm);
+                        zm[128] = gk;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ================= phase C : synthesis + overlap-add =================
+        const int tl = 2 * warp + half;      // this half-warp's frame inside the chunk
+        const int t = t0 + tl;
+        float2 head[NSIG][8];
+#pragma unroll
+        for (int sgn = 0; sgn < NSIG; ++sgn) {
+            float2 v[16];
+            float2* tile = zbuf + (tl * 2 + sgn) * 256;
+            if (t < T) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = tile[h + 16 * j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
+            }
+            __syncwarp();
+            fft256_halfwarp<true>(v, tile, prm.tw256, h);
+            // register position p holds z[m], m = h + 16 r, r = fft16_index(p): samples 2m, 2m+1
+            float2 u[16];                    // u[r], windowed + normalised
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int r = fft16_index(p);
+                const float2 w = __ldg(&prm.win_s[h + 16 * r]);
+                u[r] = make_float2(v[p].x * w.x, v[p].y * w.y);
+            }
+            // in-warp overlap: block t_lo + 1 = second half of the lower frame + first half of the upper
+            float2* tail_dst = tails + (sgn * (NW + 1) + (warp == NW - 1 ? (NW - 1) + (c & 1) : warp)) * 128;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float ux = __shfl_down_sync(0xffffffffu, u[r].x, 16);
+                const float uy = __shfl_down_sync(0xffffffffu, u[r].y, 16);
+                if (half == 0) {
+                    const float2 o = make_float2(u[8 + r].x + ux, u[8 + r].y + uy);
+                    const int beta = t + 1;  // output block, hop index beta-1 = t
+                    if (beta <= T - 1) {
+                        float* dst = out_b[sgn] + (long long)t * 256 + 2 * h + 32 * r;
+                        if (prm.vec_out) st_stream_f2(dst, o);
+                        else { st_stream_f1(dst, o.x); st_stream_f1(dst + 1, o.y); }
+                        if (sgn == 0 && t >= prm.erle_skip_hops) acc_err = fmaf(o.x, o.x, fmaf(o.y, o.y, acc_err));
+                    }
+                    head[sgn][r] = u[r];
+                } else {
+                    tail_dst[h + 16 * r] = u[8 + r];
+                }
+            }
+        }
+        __syncthreads();
+        // cross-warp overlap: block t (lower frame) = predecessor's tail + this frame's first half
+        if (half == 0 && t >= 1 && t <= T - 1) {
+#pragma unroll
+            for (int sgn = 0; sgn < NSIG; ++sgn) {
+                const float2* tail_src =
+                    tails + (sgn * (NW + 1) + (warp == 0 ? (NW - 1) + ((c + 1) & 1) : warp - 1)) * 128;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float2 tl2 = tail_src[h + 16 * r];
+                    const float2 o = make_float2(head[sgn][r].x + tl2.x, head[sgn][r].y + tl2.y);
+                    float* dst = out_b[sgn] + (long long)(t - 1) * 256 + 2 * h + 32 * r;
+                    if (prm.vec_out) st_stream_f2(dst, o);
+                    else { st_stream_f1(dst, o.x); st_stream_f1(dst + 1, o.y); }
+                    if (sgn == 0 && t - 1 >= prm.erle_skip_hops) acc_err = fmaf(o.x, o.x, fmaf(o.y, o.y, acc_err));
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: zero the output beyond (T-1)*256, ERLE ------------------------------------
+    {
+        const long long valid = (long long)(T - 1) * 256;
+        for (long long i = valid + tid; i < prm.out_stride && i < prm.L; i += NT) {
+            out_b[0][i] = 0.f;
+            if constexpr (ECHO) out_b[1][i] = 0.f;
+        }
+    }
+    if (want_erle) {
+        __syncthreads();
+        float* red = reinterpret_cast<float*>(zbuf);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc_mic += __shfl_xor_sync(0xffffffffu, acc_mic, o);
+            acc_err += __shfl_xor_sync(0xffffffffu, acc_err, o);
+        }
+        if (lane == 0) {
+            red[2 * warp] = acc_mic;
+            red[2 * warp + 1] = acc_err;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float pm = 0.f, pe = 0.f;
+            for (int w = 0; w < NW; ++w) {
+                pm += red[2 * w];
+                pe += red[2 * w + 1];
+            }
+            prm.erle_db[b] = 10.f * log10f(fmaxf(pm, 1e-20f) / fmaxf(pe, 1e-20f));
+        }
+    }
+}
+
+}  // namespace aec

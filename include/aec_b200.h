@@ -1,0 +1,138 @@
+/* aec_b200 -- C ABI of the B200-native stage-1 linear acoustic echo canceller.
+ *
+ * Drop-in boundary for the data-parallel hot path named by BASELINE.json's north_star:
+ * batched STFT framing/windowing -> partitioned frequency-domain adaptive filter (NLMS or
+ * Kalman step size) -> iSTFT -> residual / feature output for the Stage-2 model of
+ * SZU-Speech/Acoustic-Echo-Cancellation.
+ *
+ * The reference is plain Python calling torch.nn.functional; it has NO plugin / FFI
+ * interface.  Each entry point below cites the reference seam it replaces (paths relative
+ * to the reference root).  The reference contains no stage-1 filter at all: the FDAF entry
+ * points replace the (missing) step between `librosa.load` and `h5py.create_dataset` in
+ * Stage2_lhm/generate_h5files/train_wav2h5.py:20-42, and their arithmetic is the
+ * builder-authored recurrence frozen in DESIGN.md (parity unpinned by the reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - `*_run` / `aec_stft` / `aec_istft` / `aec_features` take DEVICE pointers and launch on
+ *     the caller's CUDA stream (`cuda_stream` is a cudaStream_t cast to void*, NULL = default
+ *     stream) on the CURRENT device, without synchronising.  The caller owns every buffer.
+ *   - `aec_stage1_run_host` takes HOST pointers, stages through an `aec_host_ctx`, and returns
+ *     when the outputs are in host memory.
+ *   - return 0 on success, a negative AEC_E* code otherwise; never throws, never falls
+ *     back to a CPU implementation.
+ */
+#ifndef AEC_B200_H_
+#define AEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AEC_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+    AEC_OK = 0,
+    AEC_EINVAL = -1,      /* bad argument (null pointer, negative size, ...) */
+    AEC_EUNSUPPORTED = -2, /* frame / partitions / algo combination not built */
+    AEC_ECUDA = -3,       /* a CUDA runtime call failed; see aec_last_cuda_error() */
+    AEC_ENODEVICE = -4,   /* no sm_100 device is current */
+    AEC_ENOMEM = -5
+};
+
+enum { AEC_ALGO_NLMS = 0, AEC_ALGO_KALMAN = 1 };
+
+/* Parameter block of the stage-1 filter.  frame / hop follow the reference's
+ * speech_conf (Stage2_lhm/scripts/configs.py:1-8: win_size 512, hop_size 256) and the window is
+ * the periodic Hann hard-coded at Stage2_lhm/scripts/network/ERB.py:210.  hop = frame / 2. */
+typedef struct aec_cfg {
+    int32_t frame;          /* N: 512 (16 kHz) or 1024 (48 kHz) */
+    int32_t partitions;     /* P: taps per bin, one per past hop */
+    int32_t algo;           /* AEC_ALGO_NLMS | AEC_ALGO_KALMAN */
+    float mu;               /* NLMS step size                      (default 0.5) */
+    float delta;            /* NLMS regulariser                    (default 1e-6 * frame) */
+    float kalman_a;         /* Kalman transition factor A          (default 0.999) */
+    float kalman_lambda;    /* observation-noise smoothing         (default 0.9) */
+    float kalman_c0;        /* initial covariance                  (default 1) */
+    float kalman_eps;       /* floor added to the innovation power (default 1e-10) */
+    int32_t erle_skip_hops; /* hops excluded from the ERLE sums at the start of each utterance */
+    int32_t variant;        /* 0 = library default; otherwise a tuning variant id */
+    int32_t reserved[5];
+} aec_cfg;
+
+int aec_version(void);
+const char* aec_strerror(int code);
+/* text of the last CUDA error seen by the calling thread ("" if none) */
+const char* aec_last_cuda_error(void);
+
+/* fills *cfg with the frozen defaults for the given frame length */
+int aec_cfg_default(aec_cfg* cfg, int32_t frame);
+
+/* Frame count of ConvSTFT.forward (Stage2_lhm/scripts/network/attention_ccrn.py:48-49):
+ * (n + 2*(frame-hop) - frame) / hop + 1.   Replaces the off-by-one helper
+ * countFrames (Stage2_lhm/scripts/utils/tools.py:30-32) for buffer sizing. */
+int64_t aec_num_frames(int64_t n_samples, int32_t frame);
+/* Output length of ConviSTFT.forward (attention_ccrn.py:99): (frames - 1) * hop. */
+int64_t aec_out_samples(int64_t n_samples, int32_t frame);
+
+/* Stage-1 canceller on DEVICE buffers.
+ *   far, mic   [B][in_stride]  float32, the first n_samples[b] (or L) samples are used
+ *   err        [B][out_stride] float32  time-domain error signal e = iSTFT(Y - Yhat); zero
+ *              beyond aec_out_samples(n_b) up to L
+ *   echo_est   nullable, like err: yhat = iSTFT(Yhat)
+ *   erle_db    nullable [B]: 10 log10(sum mic^2 / sum err^2) over output hops >= erle_skip_hops
+ *   n_samples  nullable DEVICE int64 [B] (ragged batch, values clamped to [0, L])
+ * in_stride, out_stride >= L.  Fast paths need 16-byte aligned rows (stride % 4 == 0 and
+ * aligned base); other layouts are handled by a slower in-kernel path, never on the CPU. */
+int aec_stage1_run(const float* far, const float* mic, float* err, float* echo_est, float* erle_db,
+                   const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride, int64_t out_stride,
+                   const aec_cfg* cfg, void* cuda_stream);
+
+/* Host-buffer variant: the call a data-prep script makes with arrays that came out of
+ * `librosa.load` (Stage2_lhm/generate_h5files/train_wav2h5.py:20-23) and whose results go to
+ * `create_dataset` (train_wav2h5.py:39-42).  Copies are pipelined against the kernel in
+ * slices of `ctx`'s capacity; pinned host memory (aec_host_alloc) gives full PCIe rate.
+ * n_samples is a HOST int64 [B] or NULL. */
+typedef struct aec_host_ctx aec_host_ctx;
+int aec_host_ctx_create(aec_host_ctx** ctx, int64_t slice_utterances, int64_t max_samples);
+int aec_host_ctx_destroy(aec_host_ctx* ctx);
+int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const float* mic, float* err, float* echo_est,
+                        float* erle_db, const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride,
+                        int64_t out_stride, const aec_cfg* cfg);
+/* page-locked host memory helpers (cudaHostAlloc / cudaFreeHost) */
+int aec_host_alloc(void** ptr, int64_t bytes);
+int aec_host_free(void* ptr);
+
+/* STFT analysis on DEVICE buffers: replaces ConvSTFT(frame, frame/2, frame, 'hann', 'complex')
+ * .forward (Stage2_lhm/scripts/network/attention_ccrn.py:45-52).
+ *   x [B][in_stride] -> spec [B][2K][T], K = frame/2+1, T = aec_num_frames(L): channels
+ *   0..K-1 real, K..2K-1 imaginary (the reference's real-over-imag layout). */
+int aec_stft(const float* x, float* spec, int64_t B, int64_t L, int64_t in_stride, int32_t frame,
+             void* cuda_stream);
+/* iSTFT synthesis: replaces ConviSTFT(...).forward (attention_ccrn.py:82-101).
+ *   spec [B][2K][T] -> y [B][out_stride], (T-1)*hop samples written per row. */
+int aec_istft(const float* spec, float* y, int64_t B, int64_t T, int64_t out_stride, int32_t frame,
+              void* cuda_stream);
+
+/* Stage-2 feature front end: replaces Little_net.forward lines
+ * Stage2_lhm/scripts/network/ERB.py:262-290 (complex STFT of mic and ref, magnitude
+ * sqrt(re^2+im^2+1e-9), @ erb, cat[mic_erb, |mic_erb - ref_erb|]).
+ *   mic, ref [B][in_stride]; erb [K][bands] row-major float32 (ERB.py:10-71);
+ *   shift_mic / shift_ref: the batch-global scalar mean/std subtracted at ERB.py:254-255
+ *   (computed by the caller; pass 0 to skip);  feat [B][T][2*bands]. */
+int aec_features(const float* mic, const float* ref, const float* erb, float* feat, int64_t B, int64_t L,
+                 int64_t in_stride, int32_t frame, int32_t bands, float shift_mic, float shift_ref,
+                 void* cuda_stream);
+
+/* Measurement helpers used by bench.py (not part of the reference-facing surface).
+ * aec_bench_fp32_peak: dependent-free FFMA loop on every SM; returns achieved FP32 TFLOP/s. */
+int aec_bench_fp32_peak(int iters, double* tflops, void* cuda_stream);
+/* number of kernels this library has launched on the calling thread since the last reset */
+int64_t aec_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEC_B200_H_ */
