@@ -1,0 +1,206 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the oracle.
+
+Bar (north star): max-abs error <= 1e-4 on the time-domain error signal, ERLE within 0.05 dB.
+STFT / iSTFT / feature front end are additionally checked against golden vectors produced by the
+reference's own operators.  The FDAF recurrence has NO reference implementation (parity unpinned):
+those cases compare against the builder-authored float64 oracle and against oracle-free properties
+at BASELINE.json's full sizes.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import acoustic_echo_cancellation_b200 as A
+from acoustic_echo_cancellation_b200 import _lib, synth
+from oracle import aec_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_ERR = 1e-4      # max abs on the time-domain error signal (north star)
+TOL_ERLE = 0.05     # dB
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _run_case(P, algo, L, B=3, ragged=False, double_talk=False, variant=0, first_u=0):
+    d = synth.make_batch(first_u, B, L, rir_len=min(P * 256, 4096), double_talk=double_talk)
+    ns = None
+    if ragged:
+        ns = np.array(([L, L - 1, max(L - 777, 1), 255, 0, 256, 257] * B)[:B], dtype=np.int64)
+    skip = 8
+    ref = O.stage1(d["far"], d["mic"], O.AecConfig(partitions=P, algo=algo), n_samples=ns, erle_skip=skip * 256)
+    cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=skip, variant=variant)
+    err, echo, erle = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg,
+                                   n_samples=None if ns is None else _cuda(ns), return_echo=True, return_erle=True)
+    torch.cuda.synchronize()
+    err, echo, erle = err.cpu().numpy(), echo.cpu().numpy(), erle.cpu().numpy()
+    n = ref["err"].shape[1]
+    if n:
+        assert np.abs(err[:, :n] - ref["err"]).max() <= TOL_ERR
+        assert np.abs(echo[:, :n] - ref["echo"]).max() <= TOL_ERR
+    assert (err[:, n:] == 0).all() and (echo[:, n:] == 0).all()
+    lens = ns if ns is not None else [L] * B
+    for b in range(B):
+        m = max(O.n_frames(int(lens[b])) - 1, 0) * 256
+        assert (err[b, m:] == 0).all()
+        if m > skip * 256:
+            assert abs(erle[b] - ref["erle_db"][b]) <= TOL_ERLE
+    return err, ref
+
+
+@pytest.mark.parametrize("P,algo", [(4, 0), (4, 1), (1, 0), (1, 1), (2, 0), (2, 1), (8, 0), (8, 1), (16, 0), (16, 1)])
+def test_stage1_matches_oracle(P, algo):
+    _run_case(P, algo, 16000)
+
+
+def test_config1_single_10s_utterance():
+    """BASELINE.json configs[0]: single 10 s 16 kHz pair, frame 512, hop 256, 4 partitions."""
+    err, ref = _run_case(4, 0, 160000, B=1)
+    assert err.shape == (1, 160000) and ref["err"].shape[1] == 160000
+
+
+def test_long_tail_kalman_10s():
+    """configs[2] algorithm (16-partition Kalman) on 10 s utterances."""
+    _run_case(16, 1, 160000, B=2)
+
+
+def test_double_talk_mixes():
+    _run_case(4, 0, 32000, double_talk=True)
+    _run_case(4, 1, 32000, double_talk=True)
+
+
+@pytest.mark.parametrize("L", [16000 + 123, 4097, 300])
+def test_ragged_and_degenerate_lengths(L):
+    _run_case(4, 0, L, B=7, ragged=True)
+
+
+@pytest.mark.parametrize("variant", [207, 206, 204, 404, 403, 108])
+def test_tuning_variants_agree(variant):
+    _run_case(4, 0, 16000 + 256, variant=variant)
+
+
+def test_unaligned_rows_take_the_in_kernel_slow_path():
+    L, B = 16001, 3
+    d = synth.make_batch(0, B, L)
+    ref = O.stage1(d["far"], d["mic"], O.AecConfig())
+    bf = torch.zeros(B, L + 3, device="cuda")
+    bm = torch.zeros(B, L + 3, device="cuda")
+    bo = torch.zeros(B, L + 3, device="cuda")
+    bf[:, 1:L + 1] = _cuda(d["far"])
+    bm[:, 1:L + 1] = _cuda(d["mic"])
+    err = A.stage1_aec(bf[:, 1:L + 1], bm[:, 1:L + 1], out=bo[:, 1:L + 1]).cpu().numpy()
+    n = ref["err"].shape[1]
+    assert np.abs(err[:, :n] - ref["err"]).max() <= TOL_ERR
+    assert float(bo[:, 0].abs().max()) == 0 and float(bo[:, L + 1:].abs().max()) == 0   # no stray writes
+
+
+def test_host_buffer_entry_matches_device_entry():
+    L, B = 16000, 10
+    d = synth.make_batch(0, B, L)
+    cfg = A.Stage1Config(erle_skip_hops=4)
+    dev, dev_erle = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg, return_erle=True)
+    pipe = A.HostPipeline(slice_utterances=4, max_samples=L)          # 3 slices, last one partial
+    err = np.empty((B, L), dtype=np.float32)
+    echo = np.empty((B, L), dtype=np.float32)
+    erle = np.empty(B, dtype=np.float32)
+    pipe.run(d["far"], d["mic"], cfg, err=err, echo=echo, erle=erle)
+    pipe.close()
+    assert np.array_equal(err, dev.cpu().numpy())
+    assert np.array_equal(erle, dev_erle.cpu().numpy())
+    assert np.abs(err + echo - d["mic"]).max() < 1e-5
+
+
+def test_unsupported_combination_is_reported_not_emulated():
+    d = synth.make_batch(0, 1, 4096)
+    with pytest.raises(A.AecError) as ei:
+        A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), A.Stage1Config(partitions=5))
+    assert ei.value.code == -2
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-pinned operators against the golden vectors
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("i", range(5))
+def test_stft_istft_match_reference_golden(golden, i):
+    x, s_ref, y_ref = golden[f"x512_{i}"], golden[f"stft512_{i}"], golden[f"istft512_{i}"]
+    s = A.ConvSTFT(512, 256, 512, "hann", "complex")(_cuda(x))
+    assert tuple(s.shape) == s_ref.shape
+    assert np.abs(s.cpu().numpy() - s_ref).max() < 5e-5       # the reference's own conv path is this far from an FFT
+    y = A.ConviSTFT(512, 256, 512, "hann", "complex")(_cuda(s_ref))
+    assert tuple(y.shape) == y_ref.shape
+    if y_ref.size:
+        assert np.abs(y.cpu().numpy() - y_ref).max() < 5e-6
+
+
+def test_istft_free_spectrum_golden(golden):
+    y = A.ConviSTFT(512, 256, 512, "hann", "complex")(_cuda(golden["spec_free"])).cpu().numpy()
+    assert np.abs(y - golden["istft_free"]).max() < 5e-6
+
+
+def test_feature_front_end_golden(golden):
+    f = A.stage2_features(_cuda(golden["feat_mic"]), _cuda(golden["feat_ref"]),
+                          _cuda(golden["erb"].astype(np.float32))).cpu().numpy()
+    assert f.shape == golden["feat"].shape
+    assert np.abs(f - golden["feat"]).max() < 2e-4 * np.abs(golden["feat"]).max()
+
+
+def test_stft_3d_input_and_ctor_errors():
+    x = torch.randn(2, 1, 2048, device="cuda")
+    s = A.ConvSTFT(512, 256, 512, "hann", "complex")(x)
+    assert tuple(s.shape) == (2, 514, 9)
+    with pytest.raises(NotImplementedError):
+        A.ConvSTFT(400, 100, 512, "hamming", "real")
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full size (configs[1]: 1024 x 10 s)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_batch():
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, L = 1024, 160000
+    far = 0.1 * torch.randn(B, L, device="cuda", generator=g)
+    mic = 0.4 * torch.roll(far, 100, dims=1) + 0.2 * torch.roll(far, 300, dims=1)
+    mic += 0.001 * torch.randn(B, L, device="cuda", generator=g)
+    return far, mic
+
+
+def test_full_size_zero_far_end_is_identity(full_batch):
+    far, mic = full_batch
+    err = A.stage1_aec(torch.zeros_like(far), mic)
+    assert float((err - mic).abs().max()) < 5e-6
+
+
+def test_full_size_nlms_linearity_and_determinism(full_batch):
+    far, mic = full_batch
+    g = torch.Generator(device="cuda").manual_seed(8)
+    mic2 = 0.05 * torch.randn(mic.shape, device="cuda", generator=g)
+    cfg = A.Stage1Config()
+    a = A.stage1_aec(far, mic, cfg)
+    b = A.stage1_aec(far, mic2, cfg)
+    c = A.stage1_aec(far, 0.5 * mic - 2.0 * mic2, cfg)
+    assert float((c - (0.5 * a - 2.0 * b)).abs().max()) < 2e-5
+    assert torch.equal(a, A.stage1_aec(far, mic, cfg))                       # run-to-run determinism
+    assert torch.isfinite(a).all()
+
+
+def test_full_size_batch_invariance_and_erle(full_batch):
+    far, mic = full_batch
+    cfg = A.Stage1Config(erle_skip_hops=125)
+    err, erle = A.stage1_aec(far, mic, cfg, return_erle=True)
+    sub, sub_erle = A.stage1_aec(far[500:503].clone(), mic[500:503].clone(), cfg, return_erle=True)
+    assert torch.equal(err[500:503], sub) and torch.equal(erle[500:503], sub_erle)
+    # echo path is a 2-tap filter well inside the 4-partition span: the canceller must converge
+    assert float(erle.min()) > 15.0
+    ref = 10 * torch.log10((mic[:, 32000:] ** 2).sum(1) / (err[:, 32000:] ** 2).sum(1))
+    assert float((ref - erle).abs().max()) < 0.05
+
+
+def test_full_size_echo_plus_error_reconstructs_mic(full_batch):
+    far, mic = full_batch
+    err, echo = A.stage1_aec(far[:256], mic[:256], A.Stage1Config(algo=A.ALGO_KALMAN), return_echo=True)
+    assert float((err + echo - mic[:256]).abs().max()) < 2e-5

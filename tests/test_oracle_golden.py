@@ -1,0 +1,56 @@
+"""CPU: the oracle's reference-pinned parts against golden vectors produced by importing the
+reference's own operators (tests/golden/make_golden.py).  Tolerances: the reference computes a
+float32 dense convolution, the oracle a float64 FFT -> ~1e-5 abs on spectra of 0.3-sigma noise."""
+import numpy as np
+import pytest
+
+from oracle import aec_oracle as O
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_stft_matches_reference_convstft(golden, i):
+    x, s = golden[f"x512_{i}"], golden[f"stft512_{i}"]
+    so = O.stft(x)
+    assert so.shape == s.shape
+    assert np.abs(so - s).max() < 5e-5
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_istft_matches_reference_convistft(golden, i):
+    s, y = golden[f"stft512_{i}"], golden[f"istft512_{i}"]
+    yo = O.istft(s.astype(np.float64))
+    assert yo.shape == y.shape
+    if y.size:
+        assert np.abs(yo - y).max() < 5e-6
+
+
+def test_istft_free_spectrum_ignores_dc_nyquist_imag(golden):
+    yo = O.istft(golden["spec_free"].astype(np.float64))
+    assert np.abs(yo - golden["istft_free"]).max() < 5e-6
+
+
+def test_frame_1024(golden):
+    so = O.stft(golden["x1024"], 1024, 512)
+    assert so.shape == golden["stft1024"].shape
+    assert np.abs(so - golden["stft1024"]).max() < 1e-4
+    yo = O.istft(golden["stft1024"].astype(np.float64), 1024, 512)
+    assert np.abs(yo - golden["istft1024"]).max() < 5e-6
+
+
+def test_frame_count_and_countframes_quirk(golden):
+    for n, t, cf in zip(golden["frame_count_L"], golden["frame_count_T"], golden["countFrames_ref"]):
+        assert O.n_frames(int(n)) == int(t)
+        assert O.count_frames_reference(int(n), 512, 256) == int(cf)
+    # the reference helper is one short of the STFT for a 10 s signal (tools.py:30-32)
+    assert O.n_frames(160000) == 626 and O.count_frames_reference(160000, 512, 256) == 625
+
+
+def test_erb_filterbank_bit_exact(golden):
+    assert np.array_equal(O.erb_filterbank(), golden["erb"])
+
+
+def test_feature_front_end(golden):
+    f = O.stage2_features(golden["feat_mic"], golden["feat_ref"], golden["erb"])
+    ref = golden["feat"]
+    assert f.shape == ref.shape
+    assert np.abs(f - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())

@@ -1,0 +1,84 @@
+"""CPU: oracle-free properties of the builder-authored recurrence and the C restatement against the
+numpy oracle.  (FDAF parity is UNPINNED by the reference: it has no stage-1 filter.)"""
+import numpy as np
+import pytest
+
+from acoustic_echo_cancellation_b200 import synth
+from oracle import aec_oracle as O
+from oracle import c_oracle as CO
+
+
+def test_zero_far_end_passes_microphone_through():
+    rng = np.random.default_rng(1)
+    mic = (0.2 * rng.standard_normal((2, 8192))).astype(np.float32)
+    for algo in (O.ALGO_NLMS, O.ALGO_KALMAN):
+        r = O.stage1(np.zeros_like(mic), mic, O.AecConfig(algo=algo))
+        assert np.abs(r["err"] - mic[:, :r["err"].shape[1]]).max() < 1e-6
+        assert np.abs(r["echo"]).max() == 0
+
+
+def test_echo_plus_error_is_stft_roundtrip_of_mic():
+    d = synth.make_batch(3, 2, 16000)
+    r = O.stage1(d["far"], d["mic"], O.AecConfig())
+    n = r["err"].shape[1]
+    assert np.abs(r["echo"] + r["err"] - d["mic"][:, :n]).max() < 1e-6
+
+
+@pytest.mark.parametrize("algo,floor", [(O.ALGO_NLMS, 10.0), (O.ALGO_KALMAN, 10.0)])
+def test_single_talk_erle_floor(algo, floor):
+    d = synth.make_batch(0, 2, 160000)
+    r = O.stage1(d["far"], d["mic"], O.AecConfig(algo=algo), erle_skip=32000)
+    assert (r["erle_db"] > floor).all(), r["erle_db"]
+
+
+def test_nlms_is_linear_in_the_microphone():
+    d = synth.make_batch(5, 1, 8192)
+    rng = np.random.default_rng(2)
+    m2 = (0.1 * rng.standard_normal((1, 8192))).astype(np.float32)
+    cfg = O.AecConfig()
+    a = O.stage1(d["far"], d["mic"], cfg)["err"]
+    b = O.stage1(d["far"], m2, cfg)["err"]
+    c = O.stage1(d["far"], 0.5 * d["mic"].astype(np.float64) - 2.0 * m2, cfg)["err"]
+    assert np.abs(c - (0.5 * a - 2.0 * b)).max() < 1e-9
+
+
+def test_float32_drift_is_far_below_tolerance():
+    d = synth.make_batch(0, 1, 160000)
+    for algo in (O.ALGO_NLMS, O.ALGO_KALMAN):
+        cfg = O.AecConfig(algo=algo)
+        a = O.stage1(d["far"], d["mic"], cfg)["err"]
+        b = O.stage1(d["far"], d["mic"], cfg, dtype=np.float32)["err"]
+        assert np.abs(a - b).max() < 2e-5
+
+
+@pytest.mark.parametrize("algo,P,L", [(0, 4, 16123), (1, 4, 16000), (1, 16, 12000), (0, 8, 8000), (0, 1, 4000)])
+def test_c_oracle_matches_numpy_oracle(algo, P, L):
+    cfg = O.AecConfig(partitions=P, algo=algo)
+    d = synth.make_batch(0, 3, L, rir_len=P * 256)
+    ns = np.array([L, L - 1, L - 777])
+    r = O.stage1(d["far"], d["mic"], cfg, n_samples=ns, erle_skip=8 * 256)
+    c = CO.stage1(d["far"], d["mic"], cfg, n_samples=ns, erle_skip_hops=8)
+    n = r["err"].shape[1]
+    assert np.abs(c["err"][:, :n] - r["err"]).max() < 1e-5
+    assert np.abs(c["echo"][:, :n] - r["echo"]).max() < 1e-5
+    assert np.abs(c["erle_db"] - r["erle_db"]).max() < 1e-3
+    assert (c["err"][:, n:] == 0).all()
+    for b in range(3):
+        m = (O.n_frames(int(ns[b])) - 1) * 256
+        assert (c["err"][b, m:] == 0).all()
+
+
+def test_ragged_equals_alone():
+    d = synth.make_batch(7, 2, 6000)
+    ns = np.array([6000, 3333])
+    r = O.stage1(d["far"], d["mic"], O.AecConfig(), n_samples=ns)
+    alone = O.stage1(d["far"][1:2, :3333], d["mic"][1:2, :3333], O.AecConfig())
+    m = alone["err"].shape[1]
+    assert np.array_equal(r["err"][1, :m], alone["err"][0])
+    assert (r["err"][1, m:] == 0).all()
+
+
+def test_flop_model_matches_survey_table():
+    assert O.flops_per_frame(O.AecConfig(partitions=4, algo=0)) == pytest.approx(56652)
+    assert O.flops_per_frame(O.AecConfig(partitions=16, algo=1)) == pytest.approx(167419)
+    assert O.flops_per_frame(O.AecConfig(frame=1024, partitions=8, algo=0)) == pytest.approx(153740)
