@@ -31,7 +31,8 @@ class AecCfg(C.Structure):
         ("kalman_eps", C.c_float),
         ("erle_skip_hops", C.c_int32),
         ("variant", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("stagger_ns", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 

@@ -238,6 +238,13 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
     auto aligned = [](const void* ptr, size_t a) { return (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) == 0; };
     p.use_tma = (aligned(far, 16) && aligned(mic, 16) && (in_stride % 4) == 0) ? 1 : 0;
     p.vec_out = (aligned(err, 8) && (!echo_est || aligned(echo_est, 8)) && (out_stride % 2) == 0) ? 1 : 0;
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        p.num_sms = sms > 0 ? sms : 148;
+        p.stagger_ns = cfg->stagger_ns < 0 ? 0 : cfg->stagger_ns;
+    }
     p.tw256 = tab.tw256;
     p.tw512 = tab.tw512;
     p.win_a = tab.win_a;
@@ -245,10 +252,11 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
 
     const int P = cfg->partitions;
     const bool echo = echo_est != nullptr;
+    // variant = 1000 * warps_per_utterance + register cap (e.g. 2144); 0 = library default
     int nw = 0, minb = 0;
     if (cfg->variant > 0) {
-        nw = cfg->variant / 100;
-        minb = cfg->variant % 100;
+        nw = cfg->variant / 1000;
+        minb = cfg->variant % 1000;
     } else {
         nw = (P <= 4) ? 2 : 4;
     }

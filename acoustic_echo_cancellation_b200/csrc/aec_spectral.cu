@@ -59,12 +59,12 @@ __device__ __forceinline__ void analyse_frame(const float* __restrict__ x, long 
 __global__ void __launch_bounds__(kThreads) stft512_kernel(const float* __restrict__ x, float* __restrict__ spec,
                                                            long long L, long long in_stride, long long T, Tables tab) {
     extern __shared__ __align__(16) unsigned char smem[];
-    float2* tiles = reinterpret_cast<float2*>(smem);                       // [8][256]
-    float* outt = reinterpret_cast<float*>(smem + 8 * 256 * sizeof(float2));  // [514][kPitch]
+    float2* tiles = reinterpret_cast<float2*>(smem);                       // [8][kTilePitch]
+    float* outt = reinterpret_cast<float*>(smem + 8 * kTilePitch * sizeof(float2));  // [514][kPitch]
     const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
     const long long b = blockIdx.y, t0 = (long long)blockIdx.x * kTT;
     const float* xb = x + b * in_stride;
-    float2* tile = tiles + hw * 256;
+    float2* tile = tiles + hw * kTilePitch;
     for (int i = 0; i < 2; ++i) {
         const int tt = hw + 8 * i;
         const long long t = t0 + tt;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) istft512_kernel(const float* __restr
                                                             long long T, long long out_stride, Tables tab) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tiles = reinterpret_cast<float2*>(smem);                        // [8][256]
-    float* inn = reinterpret_cast<float*>(smem + 8 * 256 * sizeof(float2));    // [514][kPitch], later frames [16][512]
+    float* inn = reinterpret_cast<float*>(smem + 8 * kTilePitch * sizeof(float2));    // [514][kPitch], later frames [16][512]
     const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
     const long long b = blockIdx.y, g0 = (long long)blockIdx.x * (kTT - 1);   // first output hop == first frame
     const float* sb = spec + b * (2 * kK) * T;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads) istft512_kernel(const float* __restr
         inn[c * kPitch + tt] = (g0 + tt < T) ? __ldg(sb + (long long)c * T + g0 + tt) : 0.f;
     }
     __syncthreads();
-    float2* tile = tiles + hw * 256;
+    float2* tile = tiles + hw * kTilePitch;
     float2 u[2][16];
     for (int i = 0; i < 2; ++i) {
         const int tt = hw + 8 * i;
@@ -184,12 +184,12 @@ __global__ void __launch_bounds__(kThreads) features512_kernel(const float* __re
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int kMP = 260;   // magnitude row pitch
     float2* tiles = reinterpret_cast<float2*>(smem);                             // [8][256]
-    float* mag = reinterpret_cast<float*>(smem + 8 * 256 * sizeof(float2));         // [2][kTT][kMP]
+    float* mag = reinterpret_cast<float*>(smem + 8 * kTilePitch * sizeof(float2));         // [2][kTT][kMP]
     float* erbs = mag + 2 * kTT * kMP;                                           // [257][bands]
     const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
     const long long b = blockIdx.y, t0 = (long long)blockIdx.x * kTT;
     for (int idx = tid; idx < kK * bands; idx += kThreads) erbs[idx] = __ldg(erb + idx);
-    float2* tile = tiles + hw * 256;
+    float2* tile = tiles + hw * kTilePitch;
     for (int sig = 0; sig < 2; ++sig) {
         const float* xb = (sig == 0 ? mic : ref) + b * in_stride;
         const float shift = sig == 0 ? shift_mic : shift_ref;
@@ -259,7 +259,7 @@ extern "C" int aec_stft(const float* x, float* spec, int64_t B, int64_t L, int64
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
     const long long T = aec_num_frames(L, frame);
-    const size_t smem = 8 * 256 * sizeof(float2) + (size_t)2 * kK * kPitch * sizeof(float);
+    const size_t smem = 8 * kTilePitch * sizeof(float2) + (size_t)2 * kK * kPitch * sizeof(float);
     rc = set_smem(stft512_kernel, smem);
     if (rc != AEC_OK) return rc;
     dim3 grid((unsigned)((T + kTT - 1) / kTT), (unsigned)B);
@@ -279,7 +279,7 @@ extern "C" int aec_istft(const float* spec, float* y, int64_t B, int64_t T, int6
     Tables tab;
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
-    const size_t smem = 8 * 256 * sizeof(float2) + (size_t)2 * kK * kPitch * sizeof(float);
+    const size_t smem = 8 * kTilePitch * sizeof(float2) + (size_t)2 * kK * kPitch * sizeof(float);
     rc = set_smem(istft512_kernel, smem);
     if (rc != AEC_OK) return rc;
     const long long hops = T - 1;
@@ -301,7 +301,7 @@ extern "C" int aec_features(const float* mic, const float* ref, const float* erb
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
     const long long T = aec_num_frames(L, frame);
-    const size_t smem = 8 * 256 * sizeof(float2) + (size_t)2 * kTT * 260 * sizeof(float) + (size_t)kK * bands * sizeof(float);
+    const size_t smem = 8 * kTilePitch * sizeof(float2) + (size_t)2 * kTT * 260 * sizeof(float) + (size_t)kK * bands * sizeof(float);
     rc = set_smem(features512_kernel, smem);
     if (rc != AEC_OK) return rc;
     dim3 grid((unsigned)((T + kTT - 1) / kTT), (unsigned)B);

@@ -3,7 +3,7 @@
 // A real frame of N = 512 samples is transformed through ONE 256-point complex FFT
 // (even samples -> real lane, odd samples -> imaginary lane) executed by a HALF-WARP:
 // 16 lanes x 16 complex points in registers, two radix-16 passes, one exchange through
-// a 2 KB XOR-swizzled shared-memory tile (no padding, no bank conflicts).  A warp
+// a 17-pitch padded shared-memory tile (no bank conflicts, immediate addressing).  A warp
 // therefore transforms two real frames at once (far-end + microphone on analysis,
 // two consecutive frames on synthesis).  The split into the real spectrum
 // X[0..256] (and the inverse packing) is done by the per-bin filter threads.
@@ -95,27 +95,35 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 //   h      : lane & 15
 //   v[j]   : on entry  z[h + 16 j]                 (j = 0..15)
 //            on return Z[h + 16 fft16_index(p)] in register position p
-//   tile   : 256 float2 of shared memory private to this half-warp (used as the
-//            exchange buffer; contents destroyed).  Caller guarantees every lane of the
-//            warp has finished reading whatever lived in `tile` (a __syncwarp precedes).
+//   tile   : kTilePitch (= 272) float2 of shared memory private to this half-warp, used as the
+//            exchange buffer (contents destroyed).  Rows are padded to 17 entries so both the
+//            row-wise store and the column-wise load are bank-conflict free with
+//            register + immediate addressing (no per-access index arithmetic).  Caller
+//            guarantees every lane of the warp has finished reading whatever lived in `tile`
+//            (a __syncwarp precedes).
 //   tw     : global/L1 table tw[q*16 + h] = exp(-2 pi i h q / 256)
+constexpr int kTilePitch = 272;
+
 template <bool INV>
 __device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2* tile, const float2* __restrict__ tw,
                                                 int h) {
     fft16<INV>(v);
+    float2* row = tile + h * 17;
+    const float2* twh = tw + h;
 #pragma unroll
     for (int p = 0; p < 16; ++p) {
         const int q = fft16_index(p);
         float2 x = v[p];
         if (q != 0) {
-            const float2 w = __ldg(&tw[q * 16 + h]);
+            const float2 w = __ldg(twh + q * 16);
             x = INV ? cmulc(x, w) : cmul(x, w);
         }
-        tile[h * 16 + (q ^ h)] = x;
+        row[q] = x;
     }
     __syncwarp();
+    const float2* col = tile + h;
 #pragma unroll
-    for (int l = 0; l < 16; ++l) v[l] = tile[l * 16 + (h ^ l)];
+    for (int l = 0; l < 16; ++l) v[l] = col[l * 17];
     __syncwarp();
     fft16<INV>(v);
 }

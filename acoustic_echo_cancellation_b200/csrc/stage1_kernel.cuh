@@ -43,6 +43,8 @@ struct Stage1Params {
     int erle_skip_hops;
     int use_tma;      // inputs 16-byte aligned per hop -> bulk copies
     int vec_out;      // outputs 8-byte aligned -> float2 stores
+    int stagger_ns;   // start-up skew between utterances sharing an SM (de-synchronises the phases)
+    int num_sms;
     const float2* tw256;   // [16][16]  exp(-2 pi i h q / 256) at [q*16 + h]
     const float2* tw512;   // [129]     exp(-2 pi i k / 512)
     const float2* win_a;   // [256]     0.5 * hann[2m], 0.5 * hann[2m+1]
@@ -188,14 +190,16 @@ template <int NW>
 struct Stage1Smem {
     static constexpr int F = 2 * NW;        // frames per chunk
     static constexpr int R = F + 1;         // staging ring, hops per signal
-    static constexpr size_t zbuf_bytes = size_t(F) * 2 * 256 * sizeof(float2);
+    static constexpr size_t zbuf_bytes = size_t(F) * 2 * kTilePitch * sizeof(float2);
     static constexpr size_t stage_bytes = size_t(2) * R * 256 * sizeof(float);
     __host__ __device__ static constexpr size_t tails_bytes(bool echo) { return size_t(NW + 1) * 128 * sizeof(float2) * (echo ? 2 : 1); }
     __host__ __device__ static constexpr size_t total(bool echo) { return zbuf_bytes + stage_bytes + tails_bytes(echo) + 64; }
 };
 
-template <int NW, int P, int ALGO, bool ECHO, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB) stage1_n512_kernel(const Stage1Params prm) {
+// REGS caps the registers per thread (occupancy knob: resident utterances per SM =
+// 65536 / (32 * NW * REGS), also bounded by shared memory).
+template <int NW, int P, int ALGO, bool ECHO, int REGS>
+__global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(const Stage1Params prm) {
     using SM = Stage1Smem<NW>;
     constexpr int F = SM::F, R = SM::R, NT = NW * 32;
     constexpr int PPT = 128 / NT;            // mirrored pairs per thread
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) stage1_n512_kernel(const Stage1
     constexpr int NSIG = ECHO ? 2 : 1;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* zbuf = reinterpret_cast<float2*>(smem_raw);                               // [F][2][256]
+    float2* zbuf = reinterpret_cast<float2*>(smem_raw);                               // [F][2][kTilePitch]
     float* stage = reinterpret_cast<float*>(smem_raw + SM::zbuf_bytes);               // [2][R][256]
     float2* tails = reinterpret_cast<float2*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes);  // [NSIG][NW+1][128]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes +
@@ -225,6 +229,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) stage1_n512_kernel(const Stage1
     if (tid == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
+    }
+    // Utterances resident on one SM start together and would otherwise run their FADD-heavy FFT
+    // phases and FFMA-heavy filter phases in lock-step; skew them by a fraction of a chunk.
+    if (prm.stagger_ns > 0) {
+        const unsigned slot = (unsigned)(blockIdx.x / (unsigned)prm.num_sms) & 7u;
+        if (slot) __nanosleep(slot * (unsigned)prm.stagger_ns);
     }
     __syncthreads();
 
@@ -302,7 +312,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) stage1_n512_kernel(const Stage1
                 }
                 // second half of frame t is output hop t (block t+1): inside the ERLE span?
                 if (want_erle && half == 1 && t + 1 <= T - 1 && t >= prm.erle_skip_hops) acc_mic += e_acc;
-                float2* tile = zbuf + (tl * 2 + half) * 256;
+                float2* tile = zbuf + (tl * 2 + half) * kTilePitch;
                 fft256_halfwarp<false>(v, tile, prm.tw256, h);
 #pragma unroll
                 for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
@@ -314,11 +324,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) stage1_n512_kernel(const Stage1
         if (warp == 0 && c + 1 < n_chunks) produce(t0 + F + 1, t0 + 2 * F);
 
         // ================= phase B : per-bin recurrence =================
-#pragma unroll
+        // (frame loop deliberately NOT unrolled: the whole chunk loop must fit the 32 KB
+        //  instruction cache; the price is the register moves of the history shift)
+#pragma unroll 1
         for (int tl = 0; tl < F; ++tl) {
             if (t0 + tl < T) {
-                float2* zf = zbuf + (tl * 2 + 0) * 256;
-                float2* zm = zbuf + (tl * 2 + 1) * 256;
+                float2* zf = zbuf + (tl * 2 + 0) * kTilePitch;
+                float2* zm = zbuf + (tl * 2 + 1) * kTilePitch;
 #pragma unroll
                 for (int i = 0; i < PPT; ++i) {
                     const int k = tid + i * NT;
@@ -364,7 +376,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) stage1_n512_kernel(const Stage1
 #pragma unroll
         for (int sgn = 0; sgn < NSIG; ++sgn) {
             float2 v[16];
-            float2* tile = zbuf + (tl * 2 + sgn) * 256;
+            float2* tile = zbuf + (tl * 2 + sgn) * kTilePitch;
             if (t < T) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = tile[h + 16 * j];

@@ -8,15 +8,15 @@
 
 namespace aec {
 
-// Returns cudaSuccess after launching, cudaErrorInvalidValue when (P, algo, echo, minb) is not
+// Returns cudaSuccess after launching, cudaErrorInvalidValue when (P, algo, echo, regs) is not
 // instantiated in that unit ("not built" -> AEC_EUNSUPPORTED at the ABI).
-cudaError_t launch_stage1_nw1(int P, int algo, bool echo, int minb, const Stage1Params& prm, cudaStream_t s);
-cudaError_t launch_stage1_nw2(int P, int algo, bool echo, int minb, const Stage1Params& prm, cudaStream_t s);
-cudaError_t launch_stage1_nw4(int P, int algo, bool echo, int minb, const Stage1Params& prm, cudaStream_t s);
+cudaError_t launch_stage1_nw1(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
+cudaError_t launch_stage1_nw2(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
+cudaError_t launch_stage1_nw4(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
 
-template <int NW, int P, int ALGO, bool ECHO, int MINB>
+template <int NW, int P, int ALGO, bool ECHO, int REGS>
 inline cudaError_t launch_stage1_instance(const Stage1Params& prm, cudaStream_t s) {
-    auto kern = stage1_n512_kernel<NW, P, ALGO, ECHO, MINB>;
+    auto kern = stage1_n512_kernel<NW, P, ALGO, ECHO, REGS>;
     const size_t smem = Stage1Smem<NW>::total(ECHO);
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -25,16 +25,14 @@ inline cudaError_t launch_stage1_instance(const Stage1Params& prm, cudaStream_t 
     if (configured_dev != dev) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e != cudaSuccess) return e;
         configured_dev = dev;
     }
     kern<<<dim3((unsigned)prm.B), dim3(NW * 32), smem, s>>>(prm);
     return cudaGetLastError();
 }
 
-#define AEC_TRY_INSTANCE(NW, P_, ALGO_, ECHO_, MINB_)                                         \
-    if (P == (P_) && algo == (ALGO_) && echo == (ECHO_) && (minb == (MINB_) || minb == 0))    \
-        return launch_stage1_instance<NW, P_, ALGO_, ECHO_, MINB_>(prm, s);
+#define AEC_TRY_INSTANCE(NW, P_, ALGO_, ECHO_, REGS_)                                         \
+    if (P == (P_) && algo == (ALGO_) && echo == (ECHO_) && (regs == (REGS_) || regs == 0))    \
+        return launch_stage1_instance<NW, P_, ALGO_, ECHO_, REGS_>(prm, s);
 
 }  // namespace aec

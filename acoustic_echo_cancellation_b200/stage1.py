@@ -37,6 +37,7 @@ class Stage1Config:
     kalman_eps: float = 1e-10
     erle_skip_hops: int = 0
     variant: int = 0
+    stagger_ns: int = 0
     _c: Optional[_lib.AecCfg] = field(default=None, repr=False, compare=False)
 
     @property
@@ -48,7 +49,8 @@ class Stage1Config:
             self.frame, partitions=self.partitions, algo=self.algo, mu=self.mu,
             delta=(1e-6 * self.frame if self.delta is None else self.delta),
             kalman_a=self.kalman_a, kalman_lambda=self.kalman_lambda, kalman_c0=self.kalman_c0,
-            kalman_eps=self.kalman_eps, erle_skip_hops=self.erle_skip_hops, variant=self.variant)
+            kalman_eps=self.kalman_eps, erle_skip_hops=self.erle_skip_hops, variant=self.variant,
+            stagger_ns=self.stagger_ns)
 
 
 def num_frames(n_samples: int, frame: int = 512) -> int:

@@ -58,8 +58,9 @@ typedef struct aec_cfg {
     float kalman_c0;        /* initial covariance                  (default 1) */
     float kalman_eps;       /* floor added to the innovation power (default 1e-10) */
     int32_t erle_skip_hops; /* hops excluded from the ERLE sums at the start of each utterance */
-    int32_t variant;        /* 0 = library default; otherwise a tuning variant id */
-    int32_t reserved[5];
+    int32_t variant;        /* 0 = library default; otherwise 1000*warps_per_utterance + register cap */
+    int32_t stagger_ns;     /* tuning: start-up skew between co-resident utterances; 0 = default, -1 = off */
+    int32_t reserved[4];
 } aec_cfg;
 
 int aec_version(void);

@@ -26,7 +26,7 @@ def _cuda(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
-def _run_case(P, algo, L, B=3, ragged=False, double_talk=False, variant=0, first_u=0):
+def _run_case(P, algo, L, B=3, ragged=False, double_talk=False, variant=0, first_u=0, echo=True):
     d = synth.make_batch(first_u, B, L, rir_len=min(P * 256, 4096), double_talk=double_talk)
     ns = None
     if ragged:
@@ -34,15 +34,19 @@ def _run_case(P, algo, L, B=3, ragged=False, double_talk=False, variant=0, first
     skip = 8
     ref = O.stage1(d["far"], d["mic"], O.AecConfig(partitions=P, algo=algo), n_samples=ns, erle_skip=skip * 256)
     cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=skip, variant=variant)
-    err, echo, erle = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg,
-                                   n_samples=None if ns is None else _cuda(ns), return_echo=True, return_erle=True)
+    res = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg, n_samples=None if ns is None else _cuda(ns),
+                       return_echo=echo, return_erle=True)
     torch.cuda.synchronize()
-    err, echo, erle = err.cpu().numpy(), echo.cpu().numpy(), erle.cpu().numpy()
+    err, erle = res[0].cpu().numpy(), res[-1].cpu().numpy()
     n = ref["err"].shape[1]
     if n:
         assert np.abs(err[:, :n] - ref["err"]).max() <= TOL_ERR
-        assert np.abs(echo[:, :n] - ref["echo"]).max() <= TOL_ERR
-    assert (err[:, n:] == 0).all() and (echo[:, n:] == 0).all()
+    assert (err[:, n:] == 0).all()
+    if echo:
+        ec = res[1].cpu().numpy()
+        if n:
+            assert np.abs(ec[:, :n] - ref["echo"]).max() <= TOL_ERR
+        assert (ec[:, n:] == 0).all()
     lens = ns if ns is not None else [L] * B
     for b in range(B):
         m = max(O.n_frames(int(lens[b])) - 1, 0) * 256
@@ -78,9 +82,9 @@ def test_ragged_and_degenerate_lengths(L):
     _run_case(4, 0, L, B=7, ragged=True)
 
 
-@pytest.mark.parametrize("variant", [207, 206, 204, 404, 403, 108])
+@pytest.mark.parametrize("variant", [2144, 2128, 2168, 4128, 4168, 1255])
 def test_tuning_variants_agree(variant):
-    _run_case(4, 0, 16000 + 256, variant=variant)
+    _run_case(4, 0, 16000 + 256, variant=variant, echo=False)   # tuning variants are built without the echo output
 
 
 def test_unaligned_rows_take_the_in_kernel_slow_path():
@@ -111,7 +115,8 @@ def test_host_buffer_entry_matches_device_entry():
     pipe.close()
     assert np.array_equal(err, dev.cpu().numpy())
     assert np.array_equal(erle, dev_erle.cpu().numpy())
-    assert np.abs(err + echo - d["mic"]).max() < 1e-5
+    n = A.out_samples(L)
+    assert np.abs(err + echo - d["mic"])[:, :n].max() < 1e-5
 
 
 def test_unsupported_combination_is_reported_not_emulated():

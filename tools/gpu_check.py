@@ -98,12 +98,12 @@ def spectral_cases():
     return outs
 
 
-def time_variant(variant, P=4, algo=0, B=1024, L=160000, iters=5, echo=False):
+def time_variant(variant, P=4, algo=0, B=1024, L=160000, iters=5, echo=False, stagger=0):
     g = torch.Generator(device="cuda").manual_seed(1)
     far = 0.1 * torch.randn(B, L, device="cuda", generator=g)
     mic = 0.5 * torch.roll(far, 37, dims=1) + 0.001 * torch.randn(B, L, device="cuda", generator=g)
     out = torch.empty_like(far)
-    cfg = A.Stage1Config(partitions=P, algo=algo, variant=variant)
+    cfg = A.Stage1Config(partitions=P, algo=algo, variant=variant, stagger_ns=stagger)
     try:
         for _ in range(2):
             A.stage1_aec(far, mic, cfg, out=out, return_echo=echo)
@@ -119,7 +119,7 @@ def time_variant(variant, P=4, algo=0, B=1024, L=160000, iters=5, echo=False):
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]
     best = min(ms)
     audio_s = B * L / 16000.0
-    o = {"variant": variant, "P": P, "algo": algo, "B": B, "echo": echo, "ms_best": best, "ms_med": float(np.median(ms)),
+    o = {"variant": variant, "stagger": stagger, "P": P, "algo": algo, "B": B, "echo": echo, "ms_best": best, "ms_med": float(np.median(ms)),
          "audio_s_per_s": audio_s / (best * 1e-3), "finite": bool(torch.isfinite(out).all())}
     print(json.dumps(o), flush=True)
     return o
@@ -129,7 +129,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--variants", default="207,206,205,204,403,404,402,108,110,112")
+    ap.add_argument("--variants", default="2144,2128,2168,2200,4128,4096,4168,1255,1200,1168")
+    ap.add_argument("--stagger", default="0")
+    ap.add_argument("--batches", default="1024")
     args = ap.parse_args()
     res = {"parity": [], "spectral": [], "sweep": []}
     print("device", torch.cuda.get_device_name(0), flush=True)
@@ -150,14 +152,16 @@ def main():
         res["parity"].append(parity_case("kalman P16 10s", 16, 1, 160000, B=2, echo=False))
         res["parity"].append(parity_case("nlms P4 tiny", 4, 0, 300, echo=False))
         res["parity"].append(parity_case("nlms P4 dt", 4, 0, 32000, double_talk=True))
-        for v in (206, 205, 204, 403, 404, 402, 108, 110, 112):
+        for v in (2128, 2168, 2200, 4128, 4096, 4168, 1255, 1200, 1168):
             res["parity"].append(parity_case(f"nlms P4 variant {v}", 4, 0, 16000 + 256, echo=False, variant=v))
         res["spectral"] = spectral_cases()
     print("parity time", time.time() - t0, flush=True)
     if not args.no_sweep:
         print("fp32 peak TFLOP/s", A.fp32_peak_tflops(), flush=True)
         for v in [int(x) for x in args.variants.split(",") if x]:
-            res["sweep"].append(time_variant(v))
+            for stg in [int(x) for x in args.stagger.split(",")]:
+                for bb in [int(x) for x in args.batches.split(",")]:
+                    res["sweep"].append(time_variant(v, stagger=stg, B=bb))
         res["sweep"].append(time_variant(0, P=4, algo=1))
         res["sweep"].append(time_variant(0, P=8, algo=0))
         res["sweep"].append(time_variant(0, P=16, algo=1, B=2048))
