@@ -15,6 +15,11 @@
 
 namespace aec {
 
+// Complex helpers are scalar FP32 (FADD / FMUL / FFMA).  The packed FADD2 / FMUL2 / FFMA2
+// instructions of sm_100 were tried for all of them (one issue slot per complex add, two per
+// complex multiply, +-i rotations as operand modifiers): the FFMA2 probe sustains only
+// 58 TFLOP/s against 72 TFLOP/s for scalar FFMA on this B200, register pairs cost extra moves and
+// spills, and the fused kernel got 4-6 % SLOWER -- see DESIGN.md "Rejected: packed FP32".
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -119,6 +124,40 @@ __device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2* tile, c
             x = INV ? cmulc(x, w) : cmul(x, w);
         }
         row[q] = x;
+    }
+    __syncwarp();
+    const float2* col = tile + h;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) v[l] = col[l * 17];
+    __syncwarp();
+    fft16<INV>(v);
+}
+
+// Same transform with the inter-pass twiddles generated from four per-lane registers
+// (w1, w2, w4, w8 = exp(-2 pi i h {1,2,4,8} / 256)) instead of a table: 11 extra complex
+// multiplies per call, no memory traffic and no dependence on L1 residency.
+struct TwiddleRegs {
+    float2 w1, w2, w4, w8;
+};
+
+template <bool INV>
+__device__ __forceinline__ void fft256_halfwarp_regs(float2 (&v)[16], float2* tile, const TwiddleRegs& t, int h) {
+    fft16<INV>(v);
+    float2* row = tile + h * 17;
+    // register position of output index q (inverse of fft16_index)
+    auto pos = [](int q) constexpr { return ((q & 3) << 2) | (q >> 2); };
+    auto tw = [](float2 x, float2 w) { return INV ? cmulc(x, w) : cmul(x, w); };
+    // q = low (+8): x_low *= w_low ; x_{low+8} *= w_low * w8.  Only one derived twiddle (w3) stays
+    // live, which keeps the register footprint at the four base twiddles plus a temporary.
+    row[0] = v[pos(0)];
+    row[8] = tw(v[pos(8)], t.w8);
+    const float2 w3 = cmul(t.w1, t.w2);
+#pragma unroll
+    for (int low = 1; low < 8; ++low) {
+        const float2 wl = (low == 1) ? t.w1 : (low == 2) ? t.w2 : (low == 3) ? w3 : (low == 4) ? t.w4
+                        : (low == 5) ? cmul(t.w1, t.w4) : (low == 6) ? cmul(t.w2, t.w4) : cmul(w3, t.w4);
+        row[low] = tw(v[pos(low)], wl);
+        row[low + 8] = tw(tw(v[pos(low + 8)], wl), t.w8);
     }
     __syncwarp();
     const float2* col = tile + h;

@@ -6,9 +6,9 @@ namespace aec {
 
 cudaError_t launch_stage1_nw2(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s) {
     // first match for regs == 0 is the default of that (P, algo, echo)
-    AEC_TRY_INSTANCE(2, 4, kAlgoNlms, false, 144)
-    AEC_TRY_INSTANCE(2, 4, kAlgoNlms, false, 128)
     AEC_TRY_INSTANCE(2, 4, kAlgoNlms, false, 168)
+    AEC_TRY_INSTANCE(2, 4, kAlgoNlms, false, 128)
+    AEC_TRY_INSTANCE(2, 4, kAlgoNlms, false, 144)
     AEC_TRY_INSTANCE(2, 4, kAlgoNlms, false, 200)
     AEC_TRY_INSTANCE(2, 4, kAlgoNlms, true, 168)
     AEC_TRY_INSTANCE(2, 4, kAlgoKalman, false, 168)

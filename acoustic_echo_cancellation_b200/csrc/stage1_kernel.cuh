@@ -117,6 +117,26 @@ struct BinState {
         for (int p = 0; p < (ALGO == kAlgoKalman ? P : 1); ++p) C[p] = c0;
         psi = 0.f;
     }
+    static constexpr int kFloats = 4 * P + (ALGO == kAlgoKalman ? P : 1) + 1;
+    __device__ __forceinline__ void store(float* m) const {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            m[4 * p + 0] = W[p].x; m[4 * p + 1] = W[p].y; m[4 * p + 2] = X[p].x; m[4 * p + 3] = X[p].y;
+        }
+#pragma unroll
+        for (int p = 0; p < (ALGO == kAlgoKalman ? P : 1); ++p) m[4 * P + p] = C[p];
+        m[kFloats - 1] = psi;
+    }
+    __device__ __forceinline__ void load(const float* m) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            W[p] = make_float2(m[4 * p + 0], m[4 * p + 1]);
+            X[p] = make_float2(m[4 * p + 2], m[4 * p + 3]);
+        }
+#pragma unroll
+        for (int p = 0; p < (ALGO == kAlgoKalman ? P : 1); ++p) C[p] = m[4 * P + p];
+        psi = m[kFloats - 1];
+    }
 };
 
 // One frame of the recurrence for one bin.  Operation order mirrors oracle/aec_oracle.py
@@ -192,8 +212,18 @@ struct Stage1Smem {
     static constexpr int R = F + 1;         // staging ring, hops per signal
     static constexpr size_t zbuf_bytes = size_t(F) * 2 * kTilePitch * sizeof(float2);
     static constexpr size_t stage_bytes = size_t(2) * R * 256 * sizeof(float);
-    __host__ __device__ static constexpr size_t tails_bytes(bool echo) { return size_t(NW + 1) * 128 * sizeof(float2) * (echo ? 2 : 1); }
-    __host__ __device__ static constexpr size_t total(bool echo) { return zbuf_bytes + stage_bytes + tails_bytes(echo) + 64; }
+    // window tables: analysis half-table [128] float2 + synthesis table [256] float2
+    static constexpr size_t win_bytes = size_t(128 + 256) * sizeof(float2);
+    // state of the self-mirrored bin 128 (one thread's worth; kept out of everybody's registers)
+    static constexpr size_t mid_bytes = 384;
+    // overlap-add: in-chunk tails live in the (dead after the inverse FFT) Zbuf tile of the frame
+    // that produced them; only the last warp's tail crosses a chunk boundary -> one carry slot.
+    __host__ __device__ static constexpr size_t tails_bytes(bool echo) {
+        return size_t(echo ? 2 : 1) * 128 * sizeof(float2);
+    }
+    __host__ __device__ static constexpr size_t total(bool echo) {
+        return zbuf_bytes + stage_bytes + win_bytes + tails_bytes(echo) + mid_bytes + 16;
+    }
 };
 
 // REGS caps the registers per thread (occupancy knob: resident utterances per SM =
@@ -209,9 +239,12 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);                               // [F][2][kTilePitch]
     float* stage = reinterpret_cast<float*>(smem_raw + SM::zbuf_bytes);               // [2][R][256]
-    float2* tails = reinterpret_cast<float2*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes);  // [NSIG][NW+1][128]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes +
-                                                 SM::tails_bytes(ECHO));
+    float2* win_a = reinterpret_cast<float2*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes);      // [128]
+    float2* win_s = win_a + 128;                                                               // [256]
+    float2* carry = win_s + 256;                       // [NSIG][128]   last warp's tail, crosses chunks
+    float* mid_state = reinterpret_cast<float*>(carry + NSIG * 128);                             // [<= 96]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes + SM::win_bytes +
+                                                 SM::tails_bytes(ECHO) + SM::mid_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, h = lane & 15;
@@ -272,9 +305,18 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
 
     if (warp == 0) produce(0, F);
 
+    // window tables -> shared memory (so the kernel does not depend on L1 residency: with 7
+    // utterances per SM the shared-memory carve-out leaves almost no L1), twiddles -> registers
+    for (int i = tid; i < 128; i += NT) win_a[i] = __ldg(&prm.win_a[i]);
+    for (int i = tid; i < 256; i += NT) win_s[i] = __ldg(&prm.win_s[i]);
+    TwiddleRegs twr;
+    twr.w1 = __ldg(&prm.tw256[1 * 16 + h]);
+    twr.w2 = __ldg(&prm.tw256[2 * 16 + h]);
+    twr.w4 = __ldg(&prm.tw256[4 * 16 + h]);
+    twr.w8 = __ldg(&prm.tw256[8 * 16 + h]);
+
     // ---- persistent recurrence state -------------------------------------------------------
     BinState<P, ALGO> st[2 * PPT];
-    BinState<P, ALGO> st_mid;               // bin 128, owned by the last thread
     float2 wk[PPT];
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
@@ -282,7 +324,12 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         st[2 * i + 1].init(prm.kc0);
         wk[i] = __ldg(&prm.tw512[tid + i * NT]);
     }
-    st_mid.init(prm.kc0);
+    static_assert(BinState<P, ALGO>::kFloats * sizeof(float) <= SM::mid_bytes, "mid-bin state does not fit");
+    if (tid == NT - 1) {                    // bin 128 (self-mirrored) lives in shared memory
+        BinState<P, ALGO> st_mid;
+        st_mid.init(prm.kc0);
+        st_mid.store(mid_state);
+    }
     const float2 w_mid = make_float2(0.f, -1.f);
 
     float acc_mic = 0.f, acc_err = 0.f;      // ERLE energies (mic: lanes 16-31, err: lanes 0-15)
@@ -306,14 +353,16 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float2 x = *reinterpret_cast<const float2*>((j < 8 ? s0 : s1) + 32 * (j & 7));
-                    const float2 w = __ldg(&prm.win_a[h + 16 * j]);
+                    // periodic Hann: w[n + 256] = 1 - w[n]; the table holds 0.5 w[n], n < 256
+                    float2 w = win_a[h + 16 * (j & 7)];
+                    if (j >= 8) w = make_float2(0.5f - w.x, 0.5f - w.y);
                     v[j] = make_float2(x.x * w.x, x.y * w.y);
                     if (j >= 8) e_acc = fmaf(x.x, x.x, fmaf(x.y, x.y, e_acc));
                 }
                 // second half of frame t is output hop t (block t+1): inside the ERLE span?
                 if (want_erle && half == 1 && t + 1 <= T - 1 && t >= prm.erle_skip_hops) acc_mic += e_acc;
                 float2* tile = zbuf + (tl * 2 + half) * kTilePitch;
-                fft256_halfwarp<false>(v, tile, prm.tw256, h);
+                fft256_halfwarp_regs<false>(v, tile, twr, h);
 #pragma unroll
                 for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
             }
@@ -340,9 +389,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     unpack_pair(zm[k], zm[km], wk[i], yk, ym);
                     bin_step<P, ALGO>(st[2 * i], xk, yk, prm, ek, hk);
                     bin_step<P, ALGO>(st[2 * i + 1], xm, ym, prm, em, hm);
-                    if (k == 0) {            // DC / Nyquist: imaginary parts do not contribute
-                        ek.y = 0.f; em.y = 0.f; hk.y = 0.f; hm.y = 0.f;
-                    }
+                    // (k == 0 is the DC / Nyquist pair: X, Y are exactly real there, so W, E and Yhat stay
+                    //  exactly real and need no masking of the imaginary parts before packing)
                     pack_pair(ek, em, wk[i], gk, gm);
                     zf[k] = gk;
                     zf[km] = gm;
@@ -357,7 +405,10 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     const float2 fa = zf[128], ma = zm[128];
                     unpack_pair(fa, fa, w_mid, xk, xm);
                     unpack_pair(ma, ma, w_mid, yk, ym);
+                    BinState<P, ALGO> st_mid;
+                    st_mid.load(mid_state);
                     bin_step<P, ALGO>(st_mid, xk, yk, prm, ek, hk);
+                    st_mid.store(mid_state);
                     pack_pair(ek, ek, w_mid, gk, gm);
                     zf[128] = gk;
                     if constexpr (ECHO) {
@@ -385,17 +436,18 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                 for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
             }
             __syncwarp();
-            fft256_halfwarp<true>(v, tile, prm.tw256, h);
+            fft256_halfwarp_regs<true>(v, tile, twr, h);
             // register position p holds z[m], m = h + 16 r, r = fft16_index(p): samples 2m, 2m+1
             float2 u[16];                    // u[r], windowed + normalised
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
                 const int r = fft16_index(p);
-                const float2 w = __ldg(&prm.win_s[h + 16 * r]);
+                const float2 w = win_s[h + 16 * r];
                 u[r] = make_float2(v[p].x * w.x, v[p].y * w.y);
             }
             // in-warp overlap: block t_lo + 1 = second half of the lower frame + first half of the upper
-            float2* tail_dst = tails + (sgn * (NW + 1) + (warp == NW - 1 ? (NW - 1) + (c & 1) : warp)) * 128;
+            // tail of the upper frame -> the (now dead) tile that held its spectrum
+            float2* tail_dst = zbuf + ((2 * warp + 1) * 2 + sgn) * kTilePitch;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const float ux = __shfl_down_sync(0xffffffffu, u[r].x, 16);
@@ -421,7 +473,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
 #pragma unroll
             for (int sgn = 0; sgn < NSIG; ++sgn) {
                 const float2* tail_src =
-                    tails + (sgn * (NW + 1) + (warp == 0 ? (NW - 1) + ((c + 1) & 1) : warp - 1)) * 128;
+                    (warp == 0) ? carry + sgn * 128 : zbuf + ((2 * warp - 1) * 2 + sgn) * kTilePitch;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const float2 tl2 = tail_src[h + 16 * r];
@@ -431,6 +483,17 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     else { st_stream_f1(dst, o.x); st_stream_f1(dst + 1, o.y); }
                     if (sgn == 0 && t - 1 >= prm.erle_skip_hops) acc_err = fmaf(o.x, o.x, fmaf(o.y, o.y, acc_err));
                 }
+            }
+        }
+        // the last warp's tail crosses into the next chunk: warp 0 (which has just consumed the old
+        // carry) moves it out of Zbuf before the next analysis phase overwrites the tile.
+        if (warp == 0 && c + 1 < n_chunks) {
+            __syncwarp();
+#pragma unroll
+            for (int sgn = 0; sgn < NSIG; ++sgn) {
+                const float2* src = zbuf + ((F - 1) * 2 + sgn) * kTilePitch;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) carry[sgn * 128 + lane + 32 * i] = src[lane + 32 * i];
             }
         }
     }

@@ -25,6 +25,10 @@ inline cudaError_t launch_stage1_instance(const Stage1Params& prm, cudaStream_t 
     if (configured_dev != dev) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        // The kernel keeps its tables in shared memory / registers and does not need L1: ask for
+        // the largest carve-out so that 7 two-warp utterances (31.8 KB each) fit on one SM.
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
         configured_dev = dev;
     }
     kern<<<dim3((unsigned)prm.B), dim3(NW * 32), smem, s>>>(prm);
