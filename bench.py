@@ -151,13 +151,18 @@ def cpu_arm(np, far, mic, wl, steps, warmup):
     from oracle import c_oracle as CO
 
     cfg = O.AecConfig(partitions=wl["P"], algo=wl["algo"])
-    threads = CO.load().aec_oracle_max_threads()
+    # every core this process may run on (torchrun exports OMP_NUM_THREADS=1; the explicit thread
+    # count passed to the C entry overrides it)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     out = (np.zeros_like(far), None, np.zeros(far.shape[0], dtype=np.float32))   # pre-faulted outputs
     for _ in range(warmup):
-        CO.stage1(far, mic, cfg, want_echo=False, out=out)
+        CO.stage1(far, mic, cfg, want_echo=False, out=out, n_threads=threads)
     t0 = time.perf_counter()
     for _ in range(steps):
-        CO.stage1(far, mic, cfg, want_echo=False, out=out)
+        CO.stage1(far, mic, cfg, want_echo=False, out=out, n_threads=threads)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return far.shape[0] * far.shape[1] / SR / dt, threads, dt * 1e3
 
