@@ -279,12 +279,8 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
         minb = cfg->variant % 1000;
     } else {
         nw = (P <= 4) ? 2 : 4;
-        // Short filters, two warps per utterance: 7 utterances fit on an SM only at 128 registers per
-        // thread (register file is 16K per scheduler: 4 warps x 128 x 32).  That pays when it lets the
-        // whole batch run as one resident wave (e.g. 1024 utterances on 148 SMs); larger batches
-        // run faster at 6 per SM with the roomier 168-register build (measured).
-        if (P == 4 && cfg->algo == AEC_ALGO_NLMS && !echo)
-            minb = (B <= 7LL * p.num_sms && B > 6LL * p.num_sms) ? 128 : 168;
+        // (defaults: the first instantiation listed for (P, algo, echo) in stage1_inst_nw*.cu --
+        //  128 registers for the two-warp kernels so that 7 utterances stay resident per SM)
     }
     cudaError_t e;
     switch (nw) {

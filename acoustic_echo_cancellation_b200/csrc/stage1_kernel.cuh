@@ -255,9 +255,14 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     const int n = static_cast<int>(n_ll);
     const int T = n / 256 + 1;               // frames (attention_ccrn.py:48-49 with N = 2H)
     const int n_chunks = (T + F - 1) / F;
-    const float* far_b = prm.far + b * prm.in_stride;
-    const float* mic_b = prm.mic + b * prm.in_stride;
-    float* out_b[2] = {prm.err + b * prm.out_stride, ECHO ? prm.echo + b * prm.out_stride : nullptr};
+    // Row pointers are recomputed where they are used (a handful of integer instructions per chunk)
+    // instead of living in registers across the FFT phases, where the compiler would spill them:
+    // with the 228 KB shared-memory carve-out there is no L1, so a spill reload costs an L2 round trip.
+    auto row_off = [&](long long stride) {
+        long long v = b * stride;
+        asm volatile("" : "+l"(v));          // opaque: not hoisted out of the chunk loop
+        return v;
+    };
 
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -275,6 +280,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     // [(beta-1)*256, beta*256); block 0 is the reference's left zero pad.
     auto produce = [&](int b0, int b1) {
         if (b1 > T) b1 = T;
+        const long long in_off = row_off(prm.in_stride);
+        const float* far_b = prm.far + in_off;
+        const float* mic_b = prm.mic + in_off;
         if (lane == 0) {
             int nt = 0;
             for (int beta = b0; beta <= b1; ++beta) nt += (prm.use_tma && beta >= 1 && beta * 256 <= n) ? 1 : 0;
@@ -423,6 +431,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         // ================= phase C : synthesis + overlap-add =================
         const int tl = 2 * warp + half;      // this half-warp's frame inside the chunk
         const int t = t0 + tl;
+        const long long out_off = row_off(prm.out_stride);
+        float* out_b[2] = {prm.err + out_off, ECHO ? prm.echo + out_off : nullptr};
         float2 head[NSIG][8];
 #pragma unroll
         for (int sgn = 0; sgn < NSIG; ++sgn) {
@@ -461,10 +471,12 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                         else { st_stream_f1(dst, o.x); st_stream_f1(dst + 1, o.y); }
                         if (sgn == 0 && t >= prm.erle_skip_hops) acc_err = fmaf(o.x, o.x, fmaf(o.y, o.y, acc_err));
                     }
-                    head[sgn][r] = u[r];
                 } else {
                     tail_dst[h + 16 * r] = u[8 + r];
                 }
+                // unconditional: a predicated assignment would make the old value loop-carried
+                // (16 registers live across the whole chunk loop -> spills)
+                head[sgn][r] = u[r];
             }
         }
         __syncthreads();
@@ -501,6 +513,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     // ---- epilogue: zero the output beyond (T-1)*256, ERLE ------------------------------------
     {
         const long long valid = (long long)(T - 1) * 256;
+        float* out_b[2] = {prm.err + b * prm.out_stride, ECHO ? prm.echo + b * prm.out_stride : nullptr};
         for (long long i = valid + tid; i < prm.out_stride && i < prm.L; i += NT) {
             out_b[0][i] = 0.f;
             if constexpr (ECHO) out_b[1][i] = 0.f;

@@ -82,7 +82,7 @@ def test_ragged_and_degenerate_lengths(L):
     _run_case(4, 0, L, B=7, ragged=True)
 
 
-@pytest.mark.parametrize("variant", [2144, 2128, 2168, 4128, 4168, 1255])
+@pytest.mark.parametrize("variant", [2128, 2168, 4128, 4096, 1255, 1200])
 def test_tuning_variants_agree(variant):
     _run_case(4, 0, 16000 + 256, variant=variant, echo=False)   # tuning variants are built without the echo output
 

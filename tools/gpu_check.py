@@ -129,7 +129,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--variants", default="2144,2128,2168,2200,4128,4096,4168,1255,1200,1168")
+    ap.add_argument("--variants", default="2128,2168,4128,4096,1255,1200")
     ap.add_argument("--stagger", default="0")
     ap.add_argument("--batches", default="1024")
     args = ap.parse_args()
@@ -152,7 +152,7 @@ def main():
         res["parity"].append(parity_case("kalman P16 10s", 16, 1, 160000, B=2, echo=False))
         res["parity"].append(parity_case("nlms P4 tiny", 4, 0, 300, echo=False))
         res["parity"].append(parity_case("nlms P4 dt", 4, 0, 32000, double_talk=True))
-        for v in (2128, 2168, 2200, 4128, 4096, 4168, 1255, 1200, 1168):
+        for v in (2128, 2168, 4128, 4096, 1255, 1200):
             res["parity"].append(parity_case(f"nlms P4 variant {v}", 4, 0, 16000 + 256, echo=False, variant=v))
         res["spectral"] = spectral_cases()
     print("parity time", time.time() - t0, flush=True)
