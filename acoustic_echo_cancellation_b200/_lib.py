@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaec_b200.so")
+# AEC_B200_LIB lets developer tooling A/B a differently built library; default is the in-tree build
+LIB_PATH = os.environ.get("AEC_B200_LIB") or os.path.join(_HERE, "libaec_b200.so")
 
 ALGO_NLMS = 0
 ALGO_KALMAN = 1

@@ -278,7 +278,9 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
         nw = cfg->variant / 1000;
         minb = cfg->variant % 1000;
     } else {
-        nw = (P <= 4) ? 2 : 4;
+        // measured defaults: short filters 2 warps / 2 pairs per thread; 8 partitions and
+        // more: 8 warps, one bin per thread (16-partition NLMS: 4 warps, one pair per thread)
+        nw = (P <= 4) ? 2 : (P >= 16 && cfg->algo == AEC_ALGO_NLMS) ? 4 : 8;
         // (defaults: the first instantiation listed for (P, algo, echo) in stage1_inst_nw*.cu --
         //  128 registers for the two-warp kernels so that 7 utterances stay resident per SM)
     }
@@ -287,6 +289,7 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
         case 1: e = launch_stage1_nw1(P, cfg->algo, echo, minb, p, s); break;
         case 2: e = launch_stage1_nw2(P, cfg->algo, echo, minb, p, s); break;
         case 4: e = launch_stage1_nw4(P, cfg->algo, echo, minb, p, s); break;
+        case 8: e = launch_stage1_nw8(P, cfg->algo, echo, minb, p, s); break;
         default: return AEC_EUNSUPPORTED;
     }
     if (e == cudaErrorInvalidValue) {

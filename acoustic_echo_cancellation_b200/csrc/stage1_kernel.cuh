@@ -141,11 +141,15 @@ struct BinState {
 
 // One frame of the recurrence for one bin.  Operation order mirrors oracle/aec_oracle.py
 // (fdaf_nlms / fdaf_kalman).
-template <int P, int ALGO>
+// SHIFT = false: the caller has already placed X[t-1..t-P+1] in s.X[1..P-1] (history kept in a
+// shared-memory ring for long filters, so that it is not live in registers across the FFT phases).
+template <int P, int ALGO, bool SHIFT = true>
 __device__ __forceinline__ void bin_step(BinState<P, ALGO>& s, const float2 Xn, const float2 Y,
                                          const Stage1Params& prm, float2& E, float2& Yh) {
+    if constexpr (SHIFT) {
 #pragma unroll
-    for (int p = P - 1; p > 0; --p) s.X[p] = s.X[p - 1];
+        for (int p = P - 1; p > 0; --p) s.X[p] = s.X[p - 1];
+    }
     s.X[0] = Xn;
     float2 yh = make_float2(0.f, 0.f);
 #pragma unroll
@@ -162,25 +166,26 @@ __device__ __forceinline__ void bin_step(BinState<P, ALGO>& s, const float2 Xn, 
     } else {
         const float e2 = fmaf(e.x, e.x, e.y * e.y);
         s.psi = fmaf(prm.klam, s.psi, prm.koml * e2);
-        float cx2[P];
+        // |X|^2 is recomputed in the update loop rather than kept in a P-entry array: two more
+        // instructions per tap, P fewer live registers (what decides spilling at P = 16)
         float d = 0.f;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const float x2 = fmaf(s.X[p].x, s.X[p].x, s.X[p].y * s.X[p].y);
-            cx2[p] = s.C[p] * x2;
-            d += cx2[p];
+            d = fmaf(s.C[p], x2, d);
         }
         d = d + s.psi + prm.keps;
         const float rd = __frcp_rn(d);
 #pragma unroll
         for (int p = 0; p < P; ++p) {
+            const float x2 = fmaf(s.X[p].x, s.X[p].x, s.X[p].y * s.X[p].y);
             const float gs = s.C[p] * rd;
             const float2 g = make_float2(gs * s.X[p].x, -gs * s.X[p].y);   // C conj(X) / D
             float2 w = cfma(g, e, s.W[p]);
             w = make_float2(prm.ka * w.x, prm.ka * w.y);
             s.W[p] = w;
             const float w2 = fmaf(w.x, w.x, w.y * w.y);
-            s.C[p] = fmaf(prm.ka2 * (1.f - cx2[p] * rd), s.C[p], prm.kq * w2);
+            s.C[p] = fmaf(prm.ka2 * (1.f - gs * x2), s.C[p], prm.kq * w2);
         }
     }
     E = e;
@@ -206,23 +211,28 @@ __device__ __forceinline__ void pack_pair(float2 ek, float2 em, float2 w, float2
     gm = make_float2(a.x + t.y, t.x - a.y);
 }
 
-template <int NW>
+constexpr int kRingPitch = 264;   // far-end history ring: float2 per slot (257 bins, padded)
+
+template <int NW, int P>
 struct Stage1Smem {
-    static constexpr int F = 2 * NW;        // frames per chunk
-    static constexpr int R = F + 1;         // staging ring, hops per signal
+    // long filters on the one-bin-per-thread kernel keep X[t-p] in a shared-memory ring
+    static constexpr bool kRing = (NW == 8 && P >= 16);
+    static constexpr int F = kRing ? 8 : 2 * NW;   // frames per chunk
+    static constexpr int R = F + 1;                // staging ring, hops per signal
     static constexpr size_t zbuf_bytes = size_t(F) * 2 * kTilePitch * sizeof(float2);
     static constexpr size_t stage_bytes = size_t(2) * R * 256 * sizeof(float);
     // window tables: analysis half-table [128] float2 + synthesis table [256] float2
     static constexpr size_t win_bytes = size_t(128 + 256) * sizeof(float2);
     // state of the self-mirrored bin 128 (one thread's worth; kept out of everybody's registers)
-    static constexpr size_t mid_bytes = 384;
+    static constexpr size_t mid_bytes = (size_t(P) * (8 + 8 + 4) + 4 + 15) / 16 * 16;   // W, X, C per tap (+ Psi)
+    static constexpr size_t ring_bytes = kRing ? size_t(P) * kRingPitch * sizeof(float2) : 0;
     // overlap-add: in-chunk tails live in the (dead after the inverse FFT) Zbuf tile of the frame
     // that produced them; only the last warp's tail crosses a chunk boundary -> one carry slot.
     __host__ __device__ static constexpr size_t tails_bytes(bool echo) {
         return size_t(echo ? 2 : 1) * 128 * sizeof(float2);
     }
     __host__ __device__ static constexpr size_t total(bool echo) {
-        return zbuf_bytes + stage_bytes + win_bytes + tails_bytes(echo) + mid_bytes + 16;
+        return zbuf_bytes + stage_bytes + win_bytes + tails_bytes(echo) + mid_bytes + ring_bytes + 16;
     }
 };
 
@@ -230,10 +240,16 @@ struct Stage1Smem {
 // 65536 / (32 * NW * REGS), also bounded by shared memory).
 template <int NW, int P, int ALGO, bool ECHO, int REGS>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(const Stage1Params prm) {
-    using SM = Stage1Smem<NW>;
+    using SM = Stage1Smem<NW, P>;
+    constexpr bool kRing = SM::kRing;
     constexpr int F = SM::F, R = SM::R, NT = NW * 32;
-    constexpr int PPT = 128 / NT;            // mirrored pairs per thread
-    static_assert(PPT >= 1, "at most 4 warps per utterance");
+    // NW <= 4: every thread owns PPT mirrored pairs (k, 256-k), i.e. 2*PPT bins.
+    // NW == 8: one bin per thread (long filters: the per-bin state is what fills the registers);
+    //          lanes 2i / 2i+1 hold the two bins of pair i.
+    constexpr bool kSingleBin = (NW == 8);
+    constexpr int PPT = kSingleBin ? 1 : 128 / (kSingleBin ? 128 : NT);   // mirrored pairs per thread
+    constexpr int NBIN = kSingleBin ? 1 : 2 * PPT;                        // bins per thread
+    static_assert(NW == 1 || NW == 2 || NW == 4 || NW == 8, "1, 2, 4 or 8 warps per utterance");
     constexpr int NSIG = ECHO ? 2 : 1;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -243,8 +259,10 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     float2* win_s = win_a + 128;                                                               // [256]
     float2* carry = win_s + 256;                       // [NSIG][128]   last warp's tail, crosses chunks
     float* mid_state = reinterpret_cast<float*>(carry + NSIG * 128);                             // [<= 96]
+    float2* xring = reinterpret_cast<float2*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes + SM::win_bytes +
+                                              SM::tails_bytes(ECHO) + SM::mid_bytes);        // [P][kRingPitch]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes + SM::win_bytes +
-                                                 SM::tails_bytes(ECHO) + SM::mid_bytes);
+                                                 SM::tails_bytes(ECHO) + SM::mid_bytes + SM::ring_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, h = lane & 15;
@@ -315,6 +333,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
 
     // window tables -> shared memory (so the kernel does not depend on L1 residency: with 7
     // utterances per SM the shared-memory carve-out leaves almost no L1), twiddles -> registers
+    if constexpr (kRing) {
+        for (int i = tid; i < P * kRingPitch; i += NT) xring[i] = make_float2(0.f, 0.f);   // X[t<0] = 0
+    }
     for (int i = tid; i < 128; i += NT) win_a[i] = __ldg(&prm.win_a[i]);
     for (int i = tid; i < 256; i += NT) win_s[i] = __ldg(&prm.win_s[i]);
     TwiddleRegs twr;
@@ -324,16 +345,45 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     twr.w8 = __ldg(&prm.tw256[8 * 16 + h]);
 
     // ---- persistent recurrence state -------------------------------------------------------
-    BinState<P, ALGO> st[2 * PPT];
+    BinState<P, ALGO> st[NBIN];
     float2 wk[PPT];
 #pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-        st[2 * i].init(prm.kc0);
-        st[2 * i + 1].init(prm.kc0);
-        wk[i] = __ldg(&prm.tw512[tid + i * NT]);
-    }
+    for (int i = 0; i < NBIN; ++i) st[i].init(prm.kc0);
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) wk[i] = __ldg(&prm.tw512[kSingleBin ? (tid >> 1) : tid + i * NT]);
+    // single-bin mode: the same formulas serve both bins of a pair with per-thread twiddles
+    //   unpack: X = A + wu * D,  A = own + conj(other), D = (own - conj(other)) / i
+    //           wu = w for bin k, -conj(w) for bin 256-k
+    //   pack  : G = a + i * (d * ws),  a = E_own + conj(E_other), d = E_own - conj(E_other)
+    //           ws = conj(w) for bin k, -w for bin 256-k
+    const bool side = kSingleBin && (tid & 1);
+    const float2 wu = side ? make_float2(-wk[0].x, wk[0].y) : wk[0];
+    const float2 ws = side ? make_float2(-wk[0].x, -wk[0].y) : make_float2(wk[0].x, -wk[0].y);
+    const int k_own = side ? ((256 - (tid >> 1)) & 255) : (tid >> 1);
+    const int k_oth = side ? (tid >> 1) : ((256 - (tid >> 1)) & 255);
+    const int k_bin = side ? 256 - (tid >> 1) : (tid >> 1);      // true bin index 0..256 (ring column)
+    // Bin 128 is its own mirror, the 257th bin on 256 bin slots.  The last warp runs it TAP-PARALLEL
+    // (lane p owns tap p; the sums over taps are warp reductions), with the per-tap state in shared
+    // memory: no thread carries a second bin's state in registers and the extra work is ~1/5 of a
+    // regular bin pass instead of a serial P-tap loop on one lane.
+    // (For short filters the shuffle reductions cost more than they save -- measured 3-5 % on the
+    // whole kernel -- so short filters and NLMS keep the serial form: the last thread loads / steps / stores the
+    // bin's state in shared memory.)
+    static_assert(P <= 32, "one lane per tap");
+    constexpr bool kMidTapParallel = (P >= 16 && ALGO == kAlgoKalman);   // measured: NLMS is faster serial
     static_assert(BinState<P, ALGO>::kFloats * sizeof(float) <= SM::mid_bytes, "mid-bin state does not fit");
-    if (tid == NT - 1) {                    // bin 128 (self-mirrored) lives in shared memory
+    float2* midW = reinterpret_cast<float2*>(mid_state);           // [P]
+    float2* midX = midW + P;                                       // [P]
+    float* midC = reinterpret_cast<float*>(midX + P);              // [P]
+    float* midPsi = midC + P;                                      // [1]
+    if constexpr (kMidTapParallel) {
+        if (warp == NW - 1 && lane < P) {
+            midW[lane] = make_float2(0.f, 0.f);
+            midX[lane] = make_float2(0.f, 0.f);
+            midC[lane] = prm.kc0;
+            if (lane == 0) *midPsi = 0.f;
+        }
+    } else if (tid == NT - 1) {
         BinState<P, ALGO> st_mid;
         st_mid.init(prm.kc0);
         st_mid.store(mid_state);
@@ -350,8 +400,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
 
         // ================= phase A : analysis =================
 #pragma unroll 1
-        for (int i = 0; i < 2; ++i) {
-            const int tl = warp + NW * i;
+        for (int tl = warp; tl < F; tl += NW) {
             const int t = t0 + tl;
             if (t < T) {
                 const float* s0 = stage + (half * R + (t % R)) * 256 + 2 * h;
@@ -388,6 +437,34 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
             if (t0 + tl < T) {
                 float2* zf = zbuf + (tl * 2 + 0) * kTilePitch;
                 float2* zm = zbuf + (tl * 2 + 1) * kTilePitch;
+                if constexpr (kSingleBin) {
+                    const float2 fo = zf[k_own], fx = zf[k_oth], mo = zm[k_own], mx = zm[k_oth];
+                    auto unpack1 = [&](float2 own, float2 oth) {
+                        const float2 a = make_float2(own.x + oth.x, own.y - oth.y);
+                        const float2 d = make_float2(own.y + oth.y, oth.x - own.x);
+                        return cadd(a, cmul(wu, d));
+                    };
+                    auto pack1 = [&](float2 eo) {
+                        const float2 ex = make_float2(__shfl_xor_sync(0xffffffffu, eo.x, 1),
+                                                      __shfl_xor_sync(0xffffffffu, eo.y, 1));
+                        const float2 a = make_float2(eo.x + ex.x, eo.y - ex.y);
+                        const float2 d = make_float2(eo.x - ex.x, eo.y + ex.y);
+                        const float2 t = cmul(d, ws);
+                        return make_float2(a.x - t.y, a.y + t.x);
+                    };
+                    float2 e, yh;
+                    const float2 xn = unpack1(fo, fx);
+                    if constexpr (kRing) {
+                        const int tt = t0 + tl;
+                        float2* col = xring + k_bin;
+#pragma unroll
+                        for (int p = 1; p < P; ++p) st[0].X[p] = col[((tt - p) & (P - 1)) * kRingPitch];
+                        col[(tt & (P - 1)) * kRingPitch] = xn;
+                    }
+                    bin_step<P, ALGO, !kRing>(st[0], xn, unpack1(mo, mx), prm, e, yh);
+                    zf[k_own] = pack1(e);
+                    if constexpr (ECHO) zm[k_own] = pack1(yh);
+                } else
 #pragma unroll
                 for (int i = 0; i < PPT; ++i) {
                     const int k = tid + i * NT;
@@ -408,21 +485,72 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                         zm[km] = gm;
                     }
                 }
-                if (tid == NT - 1) {         // self-mirrored bin 128
-                    float2 xk, xm, yk, ym, ek, hk, gk, gm;
-                    const float2 fa = zf[128], ma = zm[128];
-                    unpack_pair(fa, fa, w_mid, xk, xm);
-                    unpack_pair(ma, ma, w_mid, yk, ym);
-                    BinState<P, ALGO> st_mid;
-                    st_mid.load(mid_state);
-                    bin_step<P, ALGO>(st_mid, xk, yk, prm, ek, hk);
-                    st_mid.store(mid_state);
-                    pack_pair(ek, ek, w_mid, gk, gm);
-                    zf[128] = gk;
-                    if constexpr (ECHO) {
-                        pack_pair(hk, hk, w_mid, gk, gm);
-                        zm[128] = gk;
+                if constexpr (!kMidTapParallel) {
+                    if (tid == NT - 1) {     // self-mirrored bin 128, serial on the last thread
+                        float2 xk, xm, yk, ym, ek, hk, gk, gm;
+                        const float2 fa = zf[128], ma = zm[128];
+                        unpack_pair(fa, fa, w_mid, xk, xm);
+                        unpack_pair(ma, ma, w_mid, yk, ym);
+                        BinState<P, ALGO> st_mid;
+                        st_mid.load(mid_state);
+                        bin_step<P, ALGO>(st_mid, xk, yk, prm, ek, hk);
+                        st_mid.store(mid_state);
+                        pack_pair(ek, ek, w_mid, gk, gm);
+                        zf[128] = gk;
+                        if constexpr (ECHO) {
+                            pack_pair(hk, hk, w_mid, gk, gm);
+                            zm[128] = gk;
+                        }
                     }
+                } else if (warp == NW - 1) {  // self-mirrored bin 128, one lane per tap
+                    // butterfly over the (power-of-two padded) tap lanes only: log2(P) steps
+                    constexpr int kTapLanes = P <= 1 ? 1 : P <= 2 ? 2 : P <= 4 ? 4 : P <= 8 ? 8 : P <= 16 ? 16 : 32;
+                    auto wsum = [](float v) {
+#pragma unroll
+                        for (int o = kTapLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        return v;
+                    };
+                    float2 xn, yn, unused;
+                    unpack_pair(zf[128], zf[128], w_mid, xn, unused);
+                    unpack_pair(zm[128], zm[128], w_mid, yn, unused);
+                    // tap p sees the spectrum tap p-1 saw one frame ago
+                    const bool tap = lane < P;               // lanes beyond the filter length carry zeros
+                    float2 x = (lane == 0) ? xn : (tap ? midX[lane - 1] : make_float2(0.f, 0.f));
+                    float2 w = tap ? midW[lane] : make_float2(0.f, 0.f);
+                    const float2 prod = cmul(w, x);
+                    const float2 yh = make_float2(wsum(prod.x), wsum(prod.y));
+                    const float2 e = csub(yn, yh);
+                    const float x2 = fmaf(x.x, x.x, x.y * x.y);
+                    if constexpr (ALGO == kAlgoNlms) {
+                        const float g = __fdividef(prm.mu, wsum(x2) + prm.delta);
+                        w = cfmac(x, make_float2(g * e.x, g * e.y), w);
+                    } else {
+                        float c = tap ? midC[lane] : 0.f;
+                        const float psi = fmaf(prm.klam, *midPsi, prm.koml * fmaf(e.x, e.x, e.y * e.y));
+                        const float rd = __frcp_rn(wsum(c * x2) + psi + prm.keps);
+                        const float gs = c * rd;
+                        w = cfma(make_float2(gs * x.x, -gs * x.y), e, w);
+                        w = make_float2(prm.ka * w.x, prm.ka * w.y);
+                        c = fmaf(prm.ka2 * (1.f - gs * x2), c, prm.kq * fmaf(w.x, w.x, w.y * w.y));
+                        __syncwarp();
+                        if (tap) midC[lane] = c;
+                        if (lane == 0) *midPsi = psi;
+                    }
+                    __syncwarp();            // every lane has read its neighbour's X
+                    if (tap) {
+                        midX[lane] = x;
+                        midW[lane] = w;
+                    }
+                    if (lane == 0) {
+                        float2 gk, gm;
+                        pack_pair(e, e, w_mid, gk, gm);
+                        zf[128] = gk;
+                        if constexpr (ECHO) {
+                            pack_pair(yh, yh, w_mid, gk, gm);
+                            zm[128] = gk;
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -434,6 +562,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         const long long out_off = row_off(prm.out_stride);
         float* out_b[2] = {prm.err + out_off, ECHO ? prm.echo + out_off : nullptr};
         float2 head[NSIG][8];
+        const bool synth_warp = (2 * warp < F);      // F/2 frame pairs per chunk; surplus warps sit out
+        if (synth_warp)
 #pragma unroll
         for (int sgn = 0; sgn < NSIG; ++sgn) {
             float2 v[16];
@@ -481,7 +611,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         }
         __syncthreads();
         // cross-warp overlap: block t (lower frame) = predecessor's tail + this frame's first half
-        if (half == 0 && t >= 1 && t <= T - 1) {
+        if (synth_warp && half == 0 && t >= 1 && t <= T - 1) {
 #pragma unroll
             for (int sgn = 0; sgn < NSIG; ++sgn) {
                 const float2* tail_src =

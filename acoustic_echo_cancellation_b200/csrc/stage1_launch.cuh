@@ -13,11 +13,12 @@ namespace aec {
 cudaError_t launch_stage1_nw1(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
 cudaError_t launch_stage1_nw2(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
 cudaError_t launch_stage1_nw4(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
+cudaError_t launch_stage1_nw8(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
 
-template <int NW, int P, int ALGO, bool ECHO, int REGS>
+template <int NW, int P_, int ALGO, bool ECHO, int REGS>
 inline cudaError_t launch_stage1_instance(const Stage1Params& prm, cudaStream_t s) {
-    auto kern = stage1_n512_kernel<NW, P, ALGO, ECHO, REGS>;
-    const size_t smem = Stage1Smem<NW>::total(ECHO);
+    auto kern = stage1_n512_kernel<NW, P_, ALGO, ECHO, REGS>;
+    const size_t smem = Stage1Smem<NW, P_>::total(ECHO);
     static thread_local int configured_dev = -1;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);

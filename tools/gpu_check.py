@@ -154,6 +154,8 @@ def main():
         res["parity"].append(parity_case("nlms P4 dt", 4, 0, 32000, double_talk=True))
         for v in (2128, 2168, 4128, 4096, 1255, 1200):
             res["parity"].append(parity_case(f"nlms P4 variant {v}", 4, 0, 16000 + 256, echo=False, variant=v))
+        for (pp, aa) in ((16, 1), (16, 0), (8, 1), (8, 0)):
+            res["parity"].append(parity_case(f"P{pp} algo{aa} variant 8128", pp, aa, 16000 + 123, echo=True, variant=8128, ragged=True))
         res["spectral"] = spectral_cases()
     print("parity time", time.time() - t0, flush=True)
     if not args.no_sweep:
@@ -162,6 +164,12 @@ def main():
             for stg in [int(x) for x in args.stagger.split(",")]:
                 for bb in [int(x) for x in args.batches.split(",")]:
                     res["sweep"].append(time_variant(v, stagger=stg, B=bb))
+        for v in (4255, 8128):
+            res["sweep"].append(time_variant(v, P=16, algo=1, B=2048))
+            res["sweep"].append(time_variant(v, P=16, algo=0, B=2048))
+        for v in (4168, 4128, 8128):
+            res["sweep"].append(time_variant(v, P=8, algo=0, B=1024))
+            res["sweep"].append(time_variant(v, P=8, algo=1, B=1024))
         res["sweep"].append(time_variant(0, P=4, algo=1))
         res["sweep"].append(time_variant(0, P=8, algo=0))
         res["sweep"].append(time_variant(0, P=16, algo=1, B=2048))
