@@ -11,6 +11,7 @@
 
 #include "aec_common.cuh"
 #include "stage1_launch.cuh"
+#include "stage1_kernel_1024.cuh"
 
 namespace aec {
 
@@ -67,8 +68,35 @@ int build_tables(DeviceTables* dt) {
         win_s[m] = make_float2((float)syn(2 * m), (float)syn(2 * m + 1));
         win_r[m] = make_float2((float)((double)(float)w[2 * m] / 512.0), (float)((double)(float)w[2 * m + 1] / 512.0));
     }
+    // ---- frame 1024 ----
+    std::vector<float2> tw512w(17 * 32), tw1024(257), win_a1k(256), win_s1k(512);
+    for (int q = 0; q < 16; ++q)
+        for (int l = 0; l < 32; ++l) {
+            const double a = -2.0 * pi * double(l * q) / 512.0;
+            tw512w[q * 32 + l] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int a = 0; a < 32; ++a) {
+        const double ang = -2.0 * pi * double(a) / 32.0;
+        tw512w[16 * 32 + a] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    for (int k = 0; k <= 256; ++k) {
+        const double a = -2.0 * pi * double(k) / 1024.0;
+        tw1024[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    {
+        std::vector<double> w1k(1024);
+        for (int n = 0; n < 1024; ++n) w1k[n] = 0.5 - 0.5 * cos(2.0 * pi * n / 1024.0);
+        auto syn1k = [&](int n) {
+            const int m = n & 511;
+            const double wf = (double)(float)w1k[m], wb = (double)(float)w1k[m + 512];
+            return (double)(float)w1k[n] / (1024.0 * (wf * wf + wb * wb + 1e-8));
+        };
+        for (int m = 0; m < 256; ++m)
+            win_a1k[m] = make_float2((float)(0.5 * (double)(float)w1k[2 * m]), (float)(0.5 * (double)(float)w1k[2 * m + 1]));
+        for (int m = 0; m < 512; ++m) win_s1k[m] = make_float2((float)syn1k(2 * m), (float)syn1k(2 * m + 1));
+    }
     char* dev = nullptr;
-    AEC_CUDA_CHECK(cudaMalloc(&dev, 16384));
+    AEC_CUDA_CHECK(cudaMalloc(&dev, 32768));
     size_t off = 0;
     auto put = [&](const void* src, size_t n) -> const void* {
         void* dst = dev + off;
@@ -82,6 +110,10 @@ int build_tables(DeviceTables* dt) {
     dt->t.win_s = (const float2*)put(win_s.data(), 256 * sizeof(float2));
     dt->t.win_r = (const float2*)put(win_r.data(), 256 * sizeof(float2));
     dt->t.hann512 = (const float*)put(hann.data(), 512 * sizeof(float));
+    dt->t.tw512w = (const float2*)put(tw512w.data(), tw512w.size() * sizeof(float2));
+    dt->t.tw1024 = (const float2*)put(tw1024.data(), tw1024.size() * sizeof(float2));
+    dt->t.win_a1k = (const float2*)put(win_a1k.data(), win_a1k.size() * sizeof(float2));
+    dt->t.win_s1k = (const float2*)put(win_s1k.data(), win_s1k.size() * sizeof(float2));
     AEC_CUDA_CHECK(cudaGetLastError());
     dt->ready = true;
     return AEC_OK;
@@ -228,7 +260,6 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
     if (B == 0) return AEC_OK;
     if (!far || !mic || !err) return AEC_EINVAL;
     if (B > 0x7fffffffLL || L > 0x3fffffffLL) return AEC_EINVAL;
-    if (cfg->frame != 512) return AEC_EUNSUPPORTED;   // 1024-sample frames: see aec_stage1_1024.cu (next)
     Tables tab;
     rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
@@ -265,10 +296,11 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
         p.num_sms = sms > 0 ? sms : 148;
         p.stagger_ns = cfg->stagger_ns < 0 ? 0 : cfg->stagger_ns;
     }
-    p.tw256 = tab.tw256;
-    p.tw512 = tab.tw512;
-    p.win_a = tab.win_a;
-    p.win_s = tab.win_s;
+    const bool wide = cfg->frame == 1024;
+    p.tw256 = wide ? tab.tw512w : tab.tw256;
+    p.tw512 = wide ? tab.tw1024 : tab.tw512;
+    p.win_a = wide ? tab.win_a1k : tab.win_a;
+    p.win_s = wide ? tab.win_s1k : tab.win_s;
 
     const int P = cfg->partitions;
     const bool echo = echo_est != nullptr;
@@ -285,6 +317,9 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
         //  128 registers for the two-warp kernels so that 7 utterances stay resident per SM)
     }
     cudaError_t e;
+    if (wide) {
+        e = launch_stage1_1024(P, cfg->algo, echo, minb, p, s);
+    } else
     switch (nw) {
         case 1: e = launch_stage1_nw1(P, cfg->algo, echo, minb, p, s); break;
         case 2: e = launch_stage1_nw2(P, cfg->algo, echo, minb, p, s); break;

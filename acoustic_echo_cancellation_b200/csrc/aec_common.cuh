@@ -16,6 +16,11 @@ struct Tables {
     const float2* win_s;   // [256]     hann512[n] / (512 (coff[n] + 1e-8))
     const float2* win_r;   // [256]     hann512[n] / 512        (raw synthesis frame, for aec_istft)
     const float* hann512;  // [512]
+    // frame-1024 kernels
+    const float2* tw512w;  // [17][32]  rows 0..15: exp(-2 pi i l q / 512) at [q*32 + l]; row 16: exp(-2 pi i a / 32)
+    const float2* tw1024;  // [257]     exp(-2 pi i k / 1024)
+    const float2* win_a1k; // [256]     0.5 * hann1024[2m], 0.5 * hann1024[2m+1], m < 256
+    const float2* win_s1k; // [512]     hann1024[n] / (1024 (coff[n] + 1e-8))
 };
 
 // Returns AEC_OK and the tables of the current device (lazily initialised, thread safe).

@@ -167,4 +167,49 @@ __device__ __forceinline__ void fft256_halfwarp_regs(float2 (&v)[16], float2* ti
     fft16<INV>(v);
 }
 
+// ------------------------------------------------------------------------------------------
+// Full-warp 512-point complex FFT (real frames of N = 1024 samples, 48 kHz configuration).
+//   lane l holds z[l + 32 j] (j = 0..15).  512 = 16 (registers) x 2 (lane pair l, l^16) x 16
+//   (half-warp transpose):  radix-16 over j, twiddle w512^(l q), radix-2 across the lane pair with
+//   one shuffle per value (upper lanes take the difference times w32^(l & 15)), then each half-warp
+//   finishes with the transposed radix-16 pass of the 256-point kernel; half-warp b produces the
+//   outputs Z[h + 16 (2 s + b)], s = 0..15, in register position p with s = fft16_index(p).
+//   tile: 2 * kTilePitch float2 private to the warp (two padded half tiles).
+// ------------------------------------------------------------------------------------------
+struct TwiddleRegs512 {
+    float2 w1, w2, w4, w8;   // exp(-2 pi i l {1,2,4,8} / 512)
+    float2 wr;               // lanes 16..31: exp(-2 pi i (l & 15) / 32); lanes 0..15: 1
+    float sgn;               // lanes 16..31: -1 (difference); lanes 0..15: +1 (sum)
+};
+
+template <bool INV>
+__device__ __forceinline__ void fft512_warp_regs(float2 (&v)[16], float2* tile, const TwiddleRegs512& t, int lane) {
+    fft16<INV>(v);
+    const int h = lane & 15, b = lane >> 4;
+    float2* row = tile + b * kTilePitch + h * 17;
+    auto pos = [](int q) constexpr { return ((q & 3) << 2) | (q >> 2); };
+    auto tw = [](float2 x, float2 w) { return INV ? cmulc(x, w) : cmul(x, w); };
+    auto pair_step = [&](float2 x) {       // radix-2 across lanes l, l^16, then the w32 twiddle
+        const float px = __shfl_xor_sync(0xffffffffu, x.x, 16);
+        const float py = __shfl_xor_sync(0xffffffffu, x.y, 16);
+        return tw(make_float2(fmaf(t.sgn, x.x, px), fmaf(t.sgn, x.y, py)), t.wr);
+    };
+    row[0] = pair_step(v[pos(0)]);
+    row[8] = pair_step(tw(v[pos(8)], t.w8));
+    const float2 w3 = cmul(t.w1, t.w2);
+#pragma unroll
+    for (int low = 1; low < 8; ++low) {
+        const float2 wl = (low == 1) ? t.w1 : (low == 2) ? t.w2 : (low == 3) ? w3 : (low == 4) ? t.w4
+                        : (low == 5) ? cmul(t.w1, t.w4) : (low == 6) ? cmul(t.w2, t.w4) : cmul(w3, t.w4);
+        row[low] = pair_step(tw(v[pos(low)], wl));
+        row[low + 8] = pair_step(tw(tw(v[pos(low + 8)], wl), t.w8));
+    }
+    __syncwarp();
+    const float2* col = tile + b * kTilePitch + h;
+#pragma unroll
+    for (int a = 0; a < 16; ++a) v[a] = col[a * 17];
+    __syncwarp();
+    fft16<INV>(v);
+}
+
 }  // namespace aec

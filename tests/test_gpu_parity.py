@@ -26,14 +26,17 @@ def _cuda(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
-def _run_case(P, algo, L, B=3, ragged=False, double_talk=False, variant=0, first_u=0, echo=True):
-    d = synth.make_batch(first_u, B, L, rir_len=min(P * 256, 4096), double_talk=double_talk)
+def _run_case(P, algo, L, B=3, ragged=False, double_talk=False, variant=0, first_u=0, echo=True, frame=512):
+    hop = frame // 2
+    d = synth.make_batch(first_u, B, L, sample_rate=16000 * frame // 512, rir_len=min(P * hop, 4096),
+                         double_talk=double_talk)
     ns = None
     if ragged:
         ns = np.array(([L, L - 1, max(L - 777, 1), 255, 0, 256, 257] * B)[:B], dtype=np.int64)
     skip = 8
-    ref = O.stage1(d["far"], d["mic"], O.AecConfig(partitions=P, algo=algo), n_samples=ns, erle_skip=skip * 256)
-    cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=skip, variant=variant)
+    ref = O.stage1(d["far"], d["mic"], O.AecConfig(frame=frame, partitions=P, algo=algo, delta=1e-6 * frame),
+                   n_samples=ns, erle_skip=skip * hop)
+    cfg = A.Stage1Config(frame=frame, partitions=P, algo=algo, erle_skip_hops=skip, variant=variant)
     res = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg, n_samples=None if ns is None else _cuda(ns),
                        return_echo=echo, return_erle=True)
     torch.cuda.synchronize()
@@ -49,9 +52,9 @@ def _run_case(P, algo, L, B=3, ragged=False, double_talk=False, variant=0, first
         assert (ec[:, n:] == 0).all()
     lens = ns if ns is not None else [L] * B
     for b in range(B):
-        m = max(O.n_frames(int(lens[b])) - 1, 0) * 256
+        m = max(O.n_frames(int(lens[b]), frame, hop) - 1, 0) * hop
         assert (err[b, m:] == 0).all()
-        if m > skip * 256:
+        if m > skip * hop:
             assert abs(erle[b] - ref["erle_db"][b]) <= TOL_ERLE
     return err, ref
 
@@ -70,6 +73,16 @@ def test_config1_single_10s_utterance():
 def test_long_tail_kalman_10s():
     """configs[2] algorithm (16-partition Kalman) on 10 s utterances."""
     _run_case(16, 1, 160000, B=2)
+
+
+@pytest.mark.parametrize("P,algo", [(8, 0), (8, 1), (4, 0), (4, 1), (2, 0), (1, 1)])
+def test_frame_1024_matches_oracle(P, algo):
+    """BASELINE.json configs[3] geometry: 48 kHz, frame 1024, hop 512 (8 partitions is the named case)."""
+    _run_case(P, algo, 24000 + 77, ragged=True, B=4, frame=1024)
+
+
+def test_config4_48khz_double_talk_10s():
+    _run_case(8, 0, 480000, B=2, double_talk=True, frame=1024, echo=False)
 
 
 def test_double_talk_mixes():

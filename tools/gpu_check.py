@@ -20,16 +20,17 @@ from acoustic_echo_cancellation_b200 import synth  # noqa: E402
 from oracle import aec_oracle as O  # noqa: E402
 
 
-def parity_case(name, P, algo, L, B=3, ragged=False, echo=True, variant=0, unaligned=False, double_talk=False):
-    d = synth.make_batch(0, B, L, rir_len=min(P * 256, 4096), double_talk=double_talk)
+def parity_case(name, P, algo, L, B=3, ragged=False, echo=True, variant=0, unaligned=False, double_talk=False, frame=512):
+    hop = frame // 2
+    d = synth.make_batch(0, B, L, sample_rate=16000 * frame // 512, rir_len=min(P * hop, 4096), double_talk=double_talk)
     far, mic = d["far"], d["mic"]
     ns = None
     if ragged:
         ns = np.array([L, L - 1, max(L - 777, 1)][:B] + [L // 2] * max(B - 3, 0), dtype=np.int64)
-    cfg_o = O.AecConfig(partitions=P, algo=algo)
+    cfg_o = O.AecConfig(frame=frame, partitions=P, algo=algo, delta=1e-6 * frame)
     skip_hops = 8
-    ref = O.stage1(far, mic, cfg_o, n_samples=ns, erle_skip=skip_hops * 256)
-    cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=skip_hops, variant=variant)
+    ref = O.stage1(far, mic, cfg_o, n_samples=ns, erle_skip=skip_hops * hop)
+    cfg = A.Stage1Config(frame=frame, partitions=P, algo=algo, erle_skip_hops=skip_hops, variant=variant)
     if unaligned:
         buf_f = torch.zeros(B, L + 3, device="cuda")
         buf_m = torch.zeros(B, L + 3, device="cuda")
@@ -48,15 +49,15 @@ def parity_case(name, P, algo, L, B=3, ragged=False, echo=True, variant=0, unali
         ec = None
     err = err.cpu().numpy()
     lo = ref["err"].shape[1]
-    out = {"case": name, "P": P, "algo": algo, "L": L, "B": B, "variant": variant,
+    out = {"case": name, "frame": frame, "P": P, "algo": algo, "L": L, "B": B, "variant": variant,
            "max_abs_err": float(np.abs(err[:, :lo] - ref["err"]).max()) if lo else 0.0,
            "tail_zero": bool((err[:, lo:] == 0).all()),
            "erle_diff_db": float(np.abs(erle.cpu().numpy() - ref["erle_db"]).max()),
            "erle_db": [float(x) for x in ref["erle_db"]]}
     if ns is not None:
         for b in range(B):
-            m = O.n_frames(int(ns[b])) - 1
-            m = max(m, 0) * 256
+            m = O.n_frames(int(ns[b]), frame, hop) - 1
+            m = max(m, 0) * hop
             out["tail_zero"] = out["tail_zero"] and bool((err[b, m:] == 0).all())
     if ec is not None:
         out["max_abs_echo"] = float(np.abs(ec.cpu().numpy()[:, :lo] - ref["echo"]).max()) if lo else 0.0
@@ -98,12 +99,12 @@ def spectral_cases():
     return outs
 
 
-def time_variant(variant, P=4, algo=0, B=1024, L=160000, iters=5, echo=False, stagger=0):
+def time_variant(variant, P=4, algo=0, B=1024, L=160000, iters=5, echo=False, stagger=0, frame=512):
     g = torch.Generator(device="cuda").manual_seed(1)
     far = 0.1 * torch.randn(B, L, device="cuda", generator=g)
     mic = 0.5 * torch.roll(far, 37, dims=1) + 0.001 * torch.randn(B, L, device="cuda", generator=g)
     out = torch.empty_like(far)
-    cfg = A.Stage1Config(partitions=P, algo=algo, variant=variant, stagger_ns=stagger)
+    cfg = A.Stage1Config(frame=frame, partitions=P, algo=algo, variant=variant, stagger_ns=stagger)
     try:
         for _ in range(2):
             A.stage1_aec(far, mic, cfg, out=out, return_echo=echo)
@@ -118,8 +119,8 @@ def time_variant(variant, P=4, algo=0, B=1024, L=160000, iters=5, echo=False, st
     torch.cuda.synchronize()
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]
     best = min(ms)
-    audio_s = B * L / 16000.0
-    o = {"variant": variant, "stagger": stagger, "P": P, "algo": algo, "B": B, "echo": echo, "ms_best": best, "ms_med": float(np.median(ms)),
+    audio_s = B * L / (16000.0 * frame / 512)
+    o = {"variant": variant, "frame": frame, "stagger": stagger, "P": P, "algo": algo, "B": B, "echo": echo, "ms_best": best, "ms_med": float(np.median(ms)),
          "audio_s_per_s": audio_s / (best * 1e-3), "finite": bool(torch.isfinite(out).all())}
     print(json.dumps(o), flush=True)
     return o
@@ -156,6 +157,11 @@ def main():
             res["parity"].append(parity_case(f"nlms P4 variant {v}", 4, 0, 16000 + 256, echo=False, variant=v))
         for (pp, aa) in ((16, 1), (16, 0), (8, 1), (8, 0)):
             res["parity"].append(parity_case(f"P{pp} algo{aa} variant 8128", pp, aa, 16000 + 123, echo=True, variant=8128, ragged=True))
+        for (pp, aa) in ((8, 0), (8, 1), (4, 0), (4, 1), (2, 1), (1, 0)):
+            res["parity"].append(parity_case(f"frame1024 P{pp} algo{aa}", pp, aa, 24000 + 77, echo=True, ragged=True, frame=1024))
+        res["parity"].append(parity_case("frame1024 P8 10s dt", 8, 0, 480000, B=2, echo=False, frame=1024, double_talk=True))
+        res["parity"].append(parity_case("frame1024 P8 unaligned", 8, 0, 24001, echo=False, frame=1024, unaligned=True))
+        res["parity"].append(parity_case("frame1024 P4 tiny", 4, 0, 700, echo=False, frame=1024))
         res["spectral"] = spectral_cases()
     print("parity time", time.time() - t0, flush=True)
     if not args.no_sweep:
@@ -175,6 +181,8 @@ def main():
         res["sweep"].append(time_variant(0, P=16, algo=1, B=2048))
         res["sweep"].append(time_variant(0, P=4, algo=0, echo=True))
         res["sweep"].append(time_variant(0, P=4, algo=0, B=4096))
+        res["sweep"].append(time_variant(0, P=8, algo=0, B=1024, L=480000, frame=1024))
+        res["sweep"].append(time_variant(0, P=8, algo=1, B=512, L=480000, frame=1024))
         res["fp32_peak_tflops"] = A.fp32_peak_tflops()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "gpu_check.json"), "w") as f:
