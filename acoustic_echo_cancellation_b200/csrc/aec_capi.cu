@@ -179,6 +179,16 @@ __global__ void __launch_bounds__(256) ffma2_peak_kernel(float* out, int iters, 
     if (s == 123.456f) out[0] = s;
 }
 
+// int16 PCM -> float32 in [-1, 1): x / 32768, the scaling of librosa / soundfile
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const int16_t* __restrict__ src, float* __restrict__ dst,
+                                                           long long n_pairs) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+        const short2 v = reinterpret_cast<const short2*>(src)[i];
+        reinterpret_cast<float2*>(dst)[i] = make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
+    }
+}
+
 }  // namespace aec
 
 using namespace aec;
@@ -354,7 +364,23 @@ struct aec_host_ctx {
     float* d_echo[2] = {nullptr, nullptr};
     float* d_erle[2] = {nullptr, nullptr};
     long long* d_n[2] = {nullptr, nullptr};
+    int16_t* d_pcm[2] = {nullptr, nullptr};   // [2 signals][slice][stride] int16 staging (allocated on first use)
+    // page-locked staging for the small per-utterance arrays: a copy to / from pageable host memory
+    // would serialise the two-stream pipeline
+    float* h_erle[2] = {nullptr, nullptr};
+    long long* h_n[2] = {nullptr, nullptr};
+    int64_t pending_off[2] = {-1, -1};        // slice whose ERLE still sits in h_erle[k]
+    int64_t pending_nb[2] = {0, 0};
 };
+
+// drain slot k: wait for its stream, hand the staged ERLE values to the caller
+static int host_ctx_drain(aec_host_ctx* ctx, int k, float* erle_db) {
+    AEC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream[k]));
+    if (erle_db && ctx->pending_off[k] >= 0)
+        memcpy(erle_db + ctx->pending_off[k], ctx->h_erle[k], (size_t)ctx->pending_nb[k] * sizeof(float));
+    ctx->pending_off[k] = -1;
+    return AEC_OK;
+}
 
 extern "C" int aec_host_ctx_destroy(aec_host_ctx* ctx) {
     if (!ctx) return AEC_OK;
@@ -366,6 +392,9 @@ extern "C" int aec_host_ctx_destroy(aec_host_ctx* ctx) {
         cudaFree(ctx->d_echo[i]);
         cudaFree(ctx->d_erle[i]);
         cudaFree(ctx->d_n[i]);
+        cudaFree(ctx->d_pcm[i]);
+        cudaFreeHost(ctx->h_erle[i]);
+        cudaFreeHost(ctx->h_n[i]);
         if (ctx->stream[i]) cudaStreamDestroy(ctx->stream[i]);
     }
     delete ctx;
@@ -389,6 +418,8 @@ extern "C" int aec_host_ctx_create(aec_host_ctx** out, int64_t slice_utterances,
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_echo[i], sig);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_erle[i], (size_t)ctx->slice * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_n[i], (size_t)ctx->slice * sizeof(long long));
+        if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_erle[i], (size_t)ctx->slice * sizeof(float), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_n[i], (size_t)ctx->slice * sizeof(long long), cudaHostAllocDefault);
     }
     if (e != cudaSuccess) {
         set_cuda_error(e, "aec_host_ctx_create");
@@ -415,14 +446,25 @@ extern "C" int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const fl
         const int k = (int)(it & 1);
         const int64_t nb = (B - off < ctx->slice) ? (B - off) : ctx->slice;
         cudaStream_t s = ctx->stream[k];
-        // the slot's previous slice has drained when its stream has (copies were enqueued on it)
-        AEC_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_far[k], dpitch, far + off * in_stride, (size_t)in_stride * sizeof(float),
-                                         row, (size_t)nb, cudaMemcpyHostToDevice, s));
-        AEC_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_mic[k], dpitch, mic + off * in_stride, (size_t)in_stride * sizeof(float),
-                                         row, (size_t)nb, cudaMemcpyHostToDevice, s));
-        if (n_samples)
-            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n[k], n_samples + off, (size_t)nb * sizeof(int64_t),
+        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (two slices ago) is done
+        if (rc != AEC_OK) return rc;
+        // contiguous rows on both sides -> one linear copy per signal (the DMA engines run linear copies
+        // at full PCIe rate; pitched copies are only used for strided host layouts)
+        const bool lin_in = (in_stride == L) && (ctx->stride == L);
+        if (lin_in) {
+            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_far[k], far + off * in_stride, row * (size_t)nb, cudaMemcpyHostToDevice, s));
+            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_mic[k], mic + off * in_stride, row * (size_t)nb, cudaMemcpyHostToDevice, s));
+        } else {
+            AEC_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_far[k], dpitch, far + off * in_stride,
+                                             (size_t)in_stride * sizeof(float), row, (size_t)nb, cudaMemcpyHostToDevice, s));
+            AEC_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_mic[k], dpitch, mic + off * in_stride,
+                                             (size_t)in_stride * sizeof(float), row, (size_t)nb, cudaMemcpyHostToDevice, s));
+        }
+        if (n_samples) {
+            memcpy(ctx->h_n[k], n_samples + off, (size_t)nb * sizeof(int64_t));
+            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n[k], ctx->h_n[k], (size_t)nb * sizeof(int64_t),
                                            cudaMemcpyHostToDevice, s));
+        }
         rc = aec_stage1_run(ctx->d_far[k], ctx->d_mic[k], ctx->d_err[k], echo_est ? ctx->d_echo[k] : nullptr,
                             erle_db ? ctx->d_erle[k] : nullptr,
                             n_samples ? reinterpret_cast<const int64_t*>(ctx->d_n[k]) : nullptr, nb, L, ctx->stride,
@@ -431,16 +473,108 @@ extern "C" int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const fl
             first_rc = rc;
             break;
         }
-        AEC_CUDA_CHECK(cudaMemcpy2DAsync(err + off * out_stride, (size_t)out_stride * sizeof(float), ctx->d_err[k], dpitch,
-                                         row, (size_t)nb, cudaMemcpyDeviceToHost, s));
-        if (echo_est)
-            AEC_CUDA_CHECK(cudaMemcpy2DAsync(echo_est + off * out_stride, (size_t)out_stride * sizeof(float),
-                                             ctx->d_echo[k], dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
-        if (erle_db)
-            AEC_CUDA_CHECK(cudaMemcpyAsync(erle_db + off, ctx->d_erle[k], (size_t)nb * sizeof(float),
+        const bool lin_out = (out_stride == L) && (ctx->stride == L);
+        if (lin_out) {
+            AEC_CUDA_CHECK(cudaMemcpyAsync(err + off * out_stride, ctx->d_err[k], row * (size_t)nb, cudaMemcpyDeviceToHost, s));
+            if (echo_est)
+                AEC_CUDA_CHECK(cudaMemcpyAsync(echo_est + off * out_stride, ctx->d_echo[k], row * (size_t)nb,
+                                               cudaMemcpyDeviceToHost, s));
+        } else {
+            AEC_CUDA_CHECK(cudaMemcpy2DAsync(err + off * out_stride, (size_t)out_stride * sizeof(float), ctx->d_err[k],
+                                             dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
+            if (echo_est)
+                AEC_CUDA_CHECK(cudaMemcpy2DAsync(echo_est + off * out_stride, (size_t)out_stride * sizeof(float),
+                                                 ctx->d_echo[k], dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
+        }
+        if (erle_db) {
+            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->h_erle[k], ctx->d_erle[k], (size_t)nb * sizeof(float),
                                            cudaMemcpyDeviceToHost, s));
+            ctx->pending_off[k] = off;
+            ctx->pending_nb[k] = nb;
+        }
     }
-    for (int i = 0; i < 2; ++i) AEC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream[i]));
+    for (int i = 0; i < 2; ++i) {
+        rc = host_ctx_drain(ctx, i, erle_db);
+        if (rc != AEC_OK) return rc;
+    }
+    return first_rc;
+}
+
+extern "C" int aec_stage1_run_host_pcm16(aec_host_ctx* ctx, const int16_t* far, const int16_t* mic, float* err,
+                                         float* echo_est, float* erle_db, const int64_t* n_samples, int64_t B,
+                                         int64_t L, int64_t in_stride, int64_t out_stride, const aec_cfg* cfg) {
+    if (!ctx) return AEC_EINVAL;
+    int rc = validate_cfg(cfg);
+    if (rc != AEC_OK) return rc;
+    if (B < 0 || L < 0 || L > ctx->max_samples || in_stride < L || out_stride < L) return AEC_EINVAL;
+    if (B == 0) return AEC_OK;
+    if (!far || !mic || !err) return AEC_EINVAL;
+    const size_t pcm_sig = (size_t)ctx->slice * (size_t)ctx->stride;      // int16 elements per signal per slot
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->d_pcm[i]) AEC_CUDA_CHECK(cudaMalloc(&ctx->d_pcm[i], 2 * pcm_sig * sizeof(int16_t)));
+    const size_t row = (size_t)L * sizeof(float);
+    const size_t dpitch = (size_t)ctx->stride * sizeof(float);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    int first_rc = AEC_OK;
+    for (int64_t off = 0, it = 0; off < B; off += ctx->slice, ++it) {
+        const int k = (int)(it & 1);
+        const int64_t nb = (B - off < ctx->slice) ? (B - off) : ctx->slice;
+        cudaStream_t s = ctx->stream[k];
+        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (two slices ago) is done
+        if (rc != AEC_OK) return rc;
+        int16_t* pf = ctx->d_pcm[k];
+        int16_t* pm = ctx->d_pcm[k] + pcm_sig;
+        if (in_stride == L && ctx->stride == L) {
+            AEC_CUDA_CHECK(cudaMemcpyAsync(pf, far + off * in_stride, (size_t)L * 2 * (size_t)nb, cudaMemcpyHostToDevice, s));
+            AEC_CUDA_CHECK(cudaMemcpyAsync(pm, mic + off * in_stride, (size_t)L * 2 * (size_t)nb, cudaMemcpyHostToDevice, s));
+        } else {
+            AEC_CUDA_CHECK(cudaMemcpy2DAsync(pf, (size_t)ctx->stride * 2, far + off * in_stride, (size_t)in_stride * 2,
+                                             (size_t)L * 2, (size_t)nb, cudaMemcpyHostToDevice, s));
+            AEC_CUDA_CHECK(cudaMemcpy2DAsync(pm, (size_t)ctx->stride * 2, mic + off * in_stride, (size_t)in_stride * 2,
+                                             (size_t)L * 2, (size_t)nb, cudaMemcpyHostToDevice, s));
+        }
+        const long long pairs = (long long)nb * ctx->stride / 2;          // stride is a multiple of 4
+        pcm16_to_f32_kernel<<<sms * 4, 256, 0, s>>>(pf, ctx->d_far[k], pairs);
+        pcm16_to_f32_kernel<<<sms * 4, 256, 0, s>>>(pm, ctx->d_mic[k], pairs);
+        count_launch(2);
+        if (n_samples) {
+            memcpy(ctx->h_n[k], n_samples + off, (size_t)nb * sizeof(int64_t));
+            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n[k], ctx->h_n[k], (size_t)nb * sizeof(int64_t),
+                                           cudaMemcpyHostToDevice, s));
+        }
+        rc = aec_stage1_run(ctx->d_far[k], ctx->d_mic[k], ctx->d_err[k], echo_est ? ctx->d_echo[k] : nullptr,
+                            erle_db ? ctx->d_erle[k] : nullptr,
+                            n_samples ? reinterpret_cast<const int64_t*>(ctx->d_n[k]) : nullptr, nb, L, ctx->stride,
+                            ctx->stride, cfg, s);
+        if (rc != AEC_OK) {
+            first_rc = rc;
+            break;
+        }
+        if (out_stride == L && ctx->stride == L) {
+            AEC_CUDA_CHECK(cudaMemcpyAsync(err + off * out_stride, ctx->d_err[k], row * (size_t)nb, cudaMemcpyDeviceToHost, s));
+            if (echo_est)
+                AEC_CUDA_CHECK(cudaMemcpyAsync(echo_est + off * out_stride, ctx->d_echo[k], row * (size_t)nb,
+                                               cudaMemcpyDeviceToHost, s));
+        } else {
+            AEC_CUDA_CHECK(cudaMemcpy2DAsync(err + off * out_stride, (size_t)out_stride * sizeof(float), ctx->d_err[k],
+                                             dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
+            if (echo_est)
+                AEC_CUDA_CHECK(cudaMemcpy2DAsync(echo_est + off * out_stride, (size_t)out_stride * sizeof(float),
+                                                 ctx->d_echo[k], dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
+        }
+        if (erle_db) {
+            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->h_erle[k], ctx->d_erle[k], (size_t)nb * sizeof(float),
+                                           cudaMemcpyDeviceToHost, s));
+            ctx->pending_off[k] = off;
+            ctx->pending_nb[k] = nb;
+        }
+    }
+    for (int i = 0; i < 2; ++i) {
+        rc = host_ctx_drain(ctx, i, erle_db);
+        if (rc != AEC_OK) return rc;
+    }
+    AEC_CUDA_CHECK(cudaGetLastError());
     return first_rc;
 }
 

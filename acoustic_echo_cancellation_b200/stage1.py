@@ -130,8 +130,9 @@ def stage1_aec(far: torch.Tensor, mic: torch.Tensor, cfg: Optional[Stage1Config]
 
 
 class HostPipeline:
-    """Host-buffer entry (``aec_stage1_run_host``): numpy arrays in, numpy arrays out, copies
-    pipelined against the kernel in slices.  This is the call a ``create_h5``-style data-prep
+    """Host-buffer entry (``aec_stage1_run_host``; ``aec_stage1_run_host_pcm16`` for int16 PCM inputs,
+    scaled by 1/32768 on the GPU): numpy arrays in, numpy arrays out, copies pipelined against the kernel
+    in slices.  This is the call a ``create_h5``-style data-prep
     loop makes (Stage2_lhm/generate_h5files/train_wav2h5.py:20-42)."""
 
     def __init__(self, slice_utterances: int, max_samples: int, device: int = 0):
@@ -159,9 +160,11 @@ class HostPipeline:
             n_samples: Optional[np.ndarray] = None, err: Optional[np.ndarray] = None,
             echo: Optional[np.ndarray] = None, erle: Optional[np.ndarray] = None):
         cfg = cfg or Stage1Config()
+        pcm16 = far.dtype == np.int16
+        item = 2 if pcm16 else 4
         for name, a in (("far", far), ("mic", mic)):
-            if a.dtype != np.float32 or a.ndim != 2 or a.strides[1] != 4:
-                raise TypeError(f"{name} must be a 2-D float32 array with contiguous rows")
+            if a.dtype != far.dtype or a.dtype not in (np.float32, np.int16) or a.ndim != 2 or a.strides[1] != item:
+                raise TypeError(f"{name} must be a 2-D float32 (or int16 PCM) array with contiguous rows")
         if far.shape != mic.shape or far.strides[0] != mic.strides[0]:
             raise ValueError("far and mic must share shape and row stride")
         B, L = far.shape
@@ -176,14 +179,14 @@ class HostPipeline:
         if n_samples is not None:
             ns = np.ascontiguousarray(n_samples, dtype=np.int64)
         c = cfg.to_c()
+        fn = self._lib.aec_stage1_run_host_pcm16 if pcm16 else self._lib.aec_stage1_run_host
         with torch.cuda.device(self.device):
-            rc = self._lib.aec_stage1_run_host(
-                self._ctx, far.ctypes.data, mic.ctypes.data, err.ctypes.data,
-                echo.ctypes.data if echo is not None else None,
-                erle.ctypes.data if erle is not None else None,
-                ns.ctypes.data if ns is not None else None,
-                B, L, far.strides[0] // 4, err.strides[0] // 4, C.byref(c))
-        _lib.check(rc, "aec_stage1_run_host")
+            rc = fn(self._ctx, far.ctypes.data, mic.ctypes.data, err.ctypes.data,
+                    echo.ctypes.data if echo is not None else None,
+                    erle.ctypes.data if erle is not None else None,
+                    ns.ctypes.data if ns is not None else None,
+                    B, L, far.strides[0] // item, err.strides[0] // 4, C.byref(c))
+        _lib.check(rc, "aec_stage1_run_host_pcm16" if pcm16 else "aec_stage1_run_host")
         return err
 
 

@@ -102,6 +102,12 @@ int aec_host_ctx_destroy(aec_host_ctx* ctx);
 int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const float* mic, float* err, float* echo_est,
                         float* erle_db, const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride,
                         int64_t out_stride, const aec_cfg* cfg);
+/* Same call for 16-bit PCM inputs (what the wav files hold before `librosa.load` turns them into
+ * float32 = sample / 32768, train_wav2h5.py:20-23): the int16 -> float32 conversion runs on the GPU,
+ * which halves the host-to-device bytes of a PCIe-bound pipeline.  Outputs stay float32. */
+int aec_stage1_run_host_pcm16(aec_host_ctx* ctx, const int16_t* far, const int16_t* mic, float* err,
+                              float* echo_est, float* erle_db, const int64_t* n_samples, int64_t B, int64_t L,
+                              int64_t in_stride, int64_t out_stride, const aec_cfg* cfg);
 /* page-locked host memory helpers (cudaHostAlloc / cudaFreeHost) */
 int aec_host_alloc(void** ptr, int64_t bytes);
 int aec_host_free(void* ptr);

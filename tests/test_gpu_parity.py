@@ -132,6 +132,18 @@ def test_host_buffer_entry_matches_device_entry():
     assert np.abs(err + echo - d["mic"])[:, :n].max() < 1e-5
 
 
+def test_pcm16_host_entry_equals_float_entry_on_quantised_input():
+    L, B = 16000, 6
+    d = synth.make_batch(0, B, L)
+    far16 = np.round(d["far"] * 32768).clip(-32768, 32767).astype(np.int16)
+    mic16 = np.round(d["mic"] * 32768).clip(-32768, 32767).astype(np.int16)
+    pipe = A.HostPipeline(slice_utterances=4, max_samples=L)
+    e16 = pipe.run(far16, mic16)
+    ef = pipe.run(far16.astype(np.float32) / 32768, mic16.astype(np.float32) / 32768)
+    pipe.close()
+    assert np.array_equal(e16, ef)
+
+
 def test_unsupported_combination_is_reported_not_emulated():
     d = synth.make_batch(0, 1, 4096)
     with pytest.raises(A.AecError) as ei:
