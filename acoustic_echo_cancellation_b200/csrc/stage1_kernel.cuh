@@ -98,6 +98,14 @@ __device__ __forceinline__ void st_stream_f1(float* p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// MUFU.RCP without the range fix-up code of __fdividef / the Newton step of 1.0f / x (the argument
+// is a regularised power, far from the denormal / overflow ranges; 1 ulp is ample for 1e-4 parity)
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // per-bin recurrence state, resident in registers
 // ------------------------------------------------------------------------------------------
@@ -159,7 +167,7 @@ __device__ __forceinline__ void bin_step(BinState<P, ALGO>& s, const float2 Xn, 
         float pw = 0.f;
 #pragma unroll
         for (int p = 0; p < P; ++p) pw = fmaf(s.X[p].x, s.X[p].x, fmaf(s.X[p].y, s.X[p].y, pw));
-        const float g = __fdividef(prm.mu, pw + prm.delta);
+        const float g = prm.mu * rcp_fast(pw + prm.delta);
         const float2 ge = make_float2(g * e.x, g * e.y);
 #pragma unroll
         for (int p = 0; p < P; ++p) s.W[p] = cfmac(s.X[p], ge, s.W[p]);
@@ -522,7 +530,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     const float2 e = csub(yn, yh);
                     const float x2 = fmaf(x.x, x.x, x.y * x.y);
                     if constexpr (ALGO == kAlgoNlms) {
-                        const float g = __fdividef(prm.mu, wsum(x2) + prm.delta);
+                        const float g = prm.mu * rcp_fast(wsum(x2) + prm.delta);
                         w = cfmac(x, make_float2(g * e.x, g * e.y), w);
                     } else {
                         float c = tap ? midC[lane] : 0.f;
