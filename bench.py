@@ -28,12 +28,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SR = 16000
 WORKLOADS = {
     2: dict(name="configs[1]: 1024 x 10 s utterances/GPU, 16 kHz, frame 512 hop 256, 4-partition FDAF-NLMS",
-            B=1024, L=160000, P=4, algo=0),
+            B=1024, L=160000, P=4, algo=0, frame=512, sr=16000),
     3: dict(name="configs[2]: 4096 x 10 s utterances/GPU, 16 kHz, frame 512 hop 256, 16-partition Kalman FDAF",
-            B=4096, L=160000, P=16, algo=1),
+            B=4096, L=160000, P=16, algo=1, frame=512, sr=16000),
+    4: dict(name="configs[3]: 1024 x 10 s utterances/GPU, 48 kHz, frame 1024 hop 512, 8-partition FDAF-NLMS",
+            B=1024, L=480000, P=8, algo=0, frame=1024, sr=48000),
 }
 
 
@@ -106,7 +107,7 @@ def measured_peaks():
     return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
-def make_inputs_device(torch, B, L, seed, P):
+def make_inputs_device(torch, B, L, seed, P, SR=16000, hop=256):
     """SURVEY.md 8d recipe on the device (seeded): speech-like far end, exponentially decaying random
     RIR of P*256 taps, mic = echo + noise at -40 dB.  Untimed set-up."""
     g = torch.Generator(device="cuda").manual_seed(seed)
@@ -114,16 +115,17 @@ def make_inputs_device(torch, B, L, seed, P):
     mic = torch.empty(B, L, device="cuda")
     t = torch.arange(L, device="cuda", dtype=torch.float32) / SR
     env = 0.5 - 0.5 * torch.cos(2 * torch.pi * 4.0 * t)
-    nfft = 1 << (L + P * 256).bit_length()
+    nfft = 1 << (L + P * hop).bit_length()
     lp = torch.fft.rfft(0.9 ** torch.arange(128, device="cuda", dtype=torch.float32), n=nfft)
-    tau = P * 256 / 6.9
-    dec = torch.exp(-torch.arange(P * 256, device="cuda", dtype=torch.float32) / tau)
-    for b0 in range(0, B, 64):
-        nb = min(64, B - b0)
+    tau = P * hop / 6.9
+    dec = torch.exp(-torch.arange(P * hop, device="cuda", dtype=torch.float32) / tau)
+    step = 64 if L <= 200000 else 16
+    for b0 in range(0, B, step):
+        nb = min(step, B - b0)
         x = torch.randn(nb, L, device="cuda", generator=g)
         x = torch.fft.irfft(torch.fft.rfft(x, n=nfft) * lp, n=nfft)[:, :L] * env
         x = 0.5 * x / x.abs().amax(dim=1, keepdim=True)
-        h = torch.randn(nb, P * 256, device="cuda", generator=g) * dec
+        h = torch.randn(nb, P * hop, device="cuda", generator=g) * dec
         h = 0.5 * h / h.norm(dim=1, keepdim=True)
         echo = torch.fft.irfft(torch.fft.rfft(x, n=nfft) * torch.fft.rfft(h, n=nfft), n=nfft)[:, :L]
         noise = torch.randn(nb, L, device="cuda", generator=g) * echo.pow(2).mean(dim=1, keepdim=True).sqrt() * 0.01
@@ -150,7 +152,7 @@ def cpu_arm(np, far, mic, wl, steps, warmup):
     from oracle import aec_oracle as O
     from oracle import c_oracle as CO
 
-    cfg = O.AecConfig(partitions=wl["P"], algo=wl["algo"])
+    cfg = O.AecConfig(frame=wl["frame"], partitions=wl["P"], algo=wl["algo"], delta=1e-6 * wl["frame"])
     # every core this process may run on (torchrun exports OMP_NUM_THREADS=1; the explicit thread
     # count passed to the C entry overrides it)
     try:
@@ -164,7 +166,7 @@ def cpu_arm(np, far, mic, wl, steps, warmup):
     for _ in range(steps):
         CO.stage1(far, mic, cfg, want_echo=False, out=out, n_threads=threads)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return far.shape[0] * far.shape[1] / SR / dt, threads, dt * 1e3
+    return far.shape[0] * far.shape[1] / wl["sr"] / dt, threads, dt * 1e3
 
 
 def run_reference(args, wl):
@@ -226,9 +228,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B, L, P, algo = wl["B"], wl["L"], wl["P"], wl["algo"]
-    far, mic = make_inputs_device(torch, B, L, 1000 + rank, P)
+    SR, FRAME = wl["sr"], wl["frame"]
+    HOP = FRAME // 2
+    far, mic = make_inputs_device(torch, B, L, 1000 + rank, P, SR, HOP)
     err = torch.empty_like(far)
-    cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=125, variant=args.variant)
+    cfg = A.Stage1Config(frame=FRAME, partitions=P, algo=algo, erle_skip_hops=125, variant=args.variant)
     n_total = B * world
 
     def step():
@@ -337,8 +341,8 @@ def main():
         return
 
     # ---- roofline of the dominant (only) kernel ----
-    frames = L // 256 + 1
-    flops_launch = flops_per_frame(512, P, algo) * frames * B
+    frames = L // HOP + 1
+    flops_launch = flops_per_frame(FRAME, P, algo) * frames * B
     bytes_launch = 3 * 4 * L * B
     hbm_peak, hbm_src = measured_peaks()
     tf = flops_launch / (kern_ms * 1e-3) / 1e12
@@ -351,7 +355,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
-                "traffic": traffic, "kernel": "aec::stage1_n512_kernel", "kernel_ms": kern_ms,
+                "traffic": traffic, "kernel": "aec::stage1_n%d_kernel" % FRAME, "kernel_ms": kern_ms,
                 "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
                 "peak_source": "FFMA probe measured live in this run (aec_bench_fp32_peak); "
                                "MEASURED_PEAKS.json carries no FP32 figure",
@@ -378,8 +382,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (seeded on device: speech-like far end, random decaying RIR, -40 dB noise)",
         "config": {"workload": wl["name"], "utterances_per_gpu": B, "samples": L, "sample_rate": SR,
-                   "frame": 512, "hop": 256, "partitions": P, "algo": "nlms" if algo == 0 else "kalman",
-                   "l2": "inputs 1.3 GB/GPU per step >> 126 MB L2 (no flush needed)",
+                   "frame": FRAME, "hop": HOP, "partitions": P, "algo": "nlms" if algo == 0 else "kalman",
+                   "l2": "inputs %.1f GB/GPU per step >> 126 MB L2 (no flush needed)" % (2 * B * L * 4 / 1e9),
                    "parallelism": f"utterance-sharded x{world}, metrics-only all_gather"},
         "per_gpu": value / world,
         "e2e": e2e, "e2e_bitwise_equal_to_device_path": e2e_match,
