@@ -238,6 +238,144 @@ __global__ void __launch_bounds__(kThreads) features512_kernel(const float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Frame 1024 (hop 512, 513 bins): one warp per frame, 512-point complex FFT (fft512_warp_regs)
+// ---------------------------------------------------------------------------------------
+constexpr int kK1k = 513;
+constexpr int kFP1k = 2 * kTilePitch;   // float2 per warp tile
+
+__device__ __forceinline__ TwiddleRegs512 load_twiddles_1k(const Tables& tab, int lane) {
+    TwiddleRegs512 t;
+    t.w1 = __ldg(&tab.tw512w[1 * 32 + lane]);
+    t.w2 = __ldg(&tab.tw512w[2 * 32 + lane]);
+    t.w4 = __ldg(&tab.tw512w[4 * 32 + lane]);
+    t.w8 = __ldg(&tab.tw512w[8 * 32 + lane]);
+    t.wr = (lane >> 4) ? __ldg(&tab.tw512w[16 * 32 + (lane & 15)]) : make_float2(1.f, 0.f);
+    t.sgn = (lane >> 4) ? -1.f : 1.f;
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads) stft1024_kernel(const float* __restrict__ x, float* __restrict__ spec,
+                                                            long long L, long long in_stride, long long T, Tables tab) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* tiles = reinterpret_cast<float2*>(smem);                              // [4][kFP1k]
+    float* outt = reinterpret_cast<float*>(smem + 4 * kFP1k * sizeof(float2));    // [1026][kPitch]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, h = lane & 15, hb = lane >> 4;
+    const long long b = blockIdx.y, t0 = (long long)blockIdx.x * kTT;
+    const float* xb = x + b * in_stride;
+    float2* tile = tiles + warp * kFP1k;
+    const TwiddleRegs512 twr = load_twiddles_1k(tab, lane);
+    for (int i = 0; i < 4; ++i) {
+        const int tt = warp + 4 * i;
+        const long long t = t0 + tt;
+        const long long Lv = t < T ? L : 0;          // frames beyond T: zeros, never stored
+        float2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const long long sidx = (t - 1) * 512 + 2 * lane + 64 * j;
+            float2 w = __ldg(&tab.win_a1k[lane + 32 * (j & 7)]);
+            if (j >= 8) w = make_float2(0.5f - w.x, 0.5f - w.y);
+            const float x0 = (sidx >= 0 && sidx < Lv) ? __ldg(xb + sidx) : 0.f;
+            const float x1 = (sidx + 1 >= 0 && sidx + 1 < Lv) ? __ldg(xb + sidx + 1) : 0.f;
+            v[j] = make_float2(x0 * w.x, x1 * w.y);
+        }
+        __syncwarp();
+        fft512_warp_regs<false>(v, tile, twr, lane);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) tile[h + 16 * hb + 32 * fft16_index(p)] = v[p];
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = lane + 32 * q;
+            float2 xk, xm;
+            unpack_pair_s(tile[k], tile[(512 - k) & 511], __ldg(&tab.tw1024[k]), xk, xm);
+            outt[k * kPitch + tt] = xk.x;
+            outt[(kK1k + k) * kPitch + tt] = (k == 0) ? 0.f : xk.y;
+            outt[(512 - k) * kPitch + tt] = xm.x;
+            outt[(kK1k + 512 - k) * kPitch + tt] = (k == 0) ? 0.f : xm.y;
+        }
+        if (lane == 0) {
+            float2 xk, xm;
+            unpack_pair_s(tile[256], tile[256], make_float2(0.f, -1.f), xk, xm);
+            outt[256 * kPitch + tt] = xk.x;
+            outt[(kK1k + 256) * kPitch + tt] = xk.y;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    float* sb = spec + b * (2 * kK1k) * T;
+    for (int idx = tid; idx < 2 * kK1k * kTT; idx += kThreads) {
+        const int c = idx / kTT, tt = idx % kTT;
+        if (t0 + tt < T) sb[(long long)c * T + t0 + tt] = outt[c * kPitch + tt];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) istft1024_kernel(const float* __restrict__ spec, float* __restrict__ y,
+                                                             long long T, long long out_stride, Tables tab) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* tiles = reinterpret_cast<float2*>(smem);                                           // [4][kFP1k]
+    float* inn = reinterpret_cast<float*>(smem + 4 * kFP1k * sizeof(float2));                  // [1026][kPitch]
+    float2* fr = reinterpret_cast<float2*>(smem + 4 * kFP1k * sizeof(float2) + (size_t)2 * kK1k * kPitch * sizeof(float));  // [16][512]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, h = lane & 15, hb = lane >> 4;
+    const long long b = blockIdx.y, g0 = (long long)blockIdx.x * (kTT - 1);
+    const float* sb = spec + b * (2 * kK1k) * T;
+    for (int idx = tid; idx < 2 * kK1k * kTT; idx += kThreads) {
+        const int c = idx / kTT, tt = idx % kTT;
+        inn[c * kPitch + tt] = (g0 + tt < T) ? __ldg(sb + (long long)c * T + g0 + tt) : 0.f;
+    }
+    __syncthreads();
+    float2* tile = tiles + warp * kFP1k;
+    const TwiddleRegs512 twr = load_twiddles_1k(tab, lane);
+    for (int i = 0; i < 4; ++i) {
+        const int tt = warp + 4 * i;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = lane + 32 * q;
+            float2 ek = make_float2(inn[k * kPitch + tt], inn[(kK1k + k) * kPitch + tt]);
+            float2 em = make_float2(inn[(512 - k) * kPitch + tt], inn[(kK1k + 512 - k) * kPitch + tt]);
+            if (k == 0) {
+                ek.y = 0.f;
+                em.y = 0.f;
+            }
+            float2 gk, gm;
+            pack_pair_s(ek, em, __ldg(&tab.tw1024[k]), gk, gm);
+            tile[k] = gk;
+            tile[(512 - k) & 511] = gm;
+        }
+        if (lane == 0) {
+            const float2 e = make_float2(inn[256 * kPitch + tt], inn[(kK1k + 256) * kPitch + tt]);
+            float2 gk, gm;
+            pack_pair_s(e, e, make_float2(0.f, -1.f), gk, gm);
+            tile[256] = gk;
+        }
+        __syncwarp();
+        float2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = tile[lane + 32 * j];
+        __syncwarp();
+        fft512_warp_regs<true>(v, tile, twr, lane);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const int m = h + 16 * hb + 32 * fft16_index(p);
+            const float2 w = __ldg(&tab.win_s1k[m]);
+            fr[tt * 512 + m] = make_float2(v[p].x * w.x, v[p].y * w.y);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    float* yb = y + b * out_stride;
+    for (int idx = tid; idx < (kTT - 1) * 256; idx += kThreads) {
+        const int tt = idx / 256, m = idx % 256;
+        const long long g = g0 + tt;
+        if (g + 1 <= T - 1) {
+            const float2 a = fr[tt * 512 + 256 + m];
+            const float2 c = fr[(tt + 1) * 512 + m];
+            yb[g * 512 + 2 * m] = a.x + c.x;
+            yb[g * 512 + 2 * m + 1] = a.y + c.y;
+        }
+    }
+}
+
 template <typename K>
 int set_smem(K kern, size_t bytes) {
     AEC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -252,13 +390,23 @@ using namespace aec;
 extern "C" int aec_stft(const float* x, float* spec, int64_t B, int64_t L, int64_t in_stride, int32_t frame,
                         void* cuda_stream) {
     if (B < 0 || L < 0 || in_stride < L) return AEC_EINVAL;
-    if (frame != 512) return frame == 1024 ? AEC_EUNSUPPORTED : AEC_EINVAL;
+    if (frame != 512 && frame != 1024) return AEC_EINVAL;
     if (B == 0) return AEC_OK;
     if (!x || !spec || B > 65535) return AEC_EINVAL;
     Tables tab;
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
     const long long T = aec_num_frames(L, frame);
+    if (frame == 1024) {
+        const size_t smem1k = 4 * kFP1k * sizeof(float2) + (size_t)2 * kK1k * kPitch * sizeof(float);
+        rc = set_smem(stft1024_kernel, smem1k);
+        if (rc != AEC_OK) return rc;
+        dim3 grid1k((unsigned)((T + kTT - 1) / kTT), (unsigned)B);
+        stft1024_kernel<<<grid1k, kThreads, smem1k, static_cast<cudaStream_t>(cuda_stream)>>>(x, spec, L, in_stride, T, tab);
+        AEC_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        return AEC_OK;
+    }
     const size_t smem = 8 * kTilePitch * sizeof(float2) + (size_t)2 * kK * kPitch * sizeof(float);
     rc = set_smem(stft512_kernel, smem);
     if (rc != AEC_OK) return rc;
@@ -272,13 +420,24 @@ extern "C" int aec_stft(const float* x, float* spec, int64_t B, int64_t L, int64
 extern "C" int aec_istft(const float* spec, float* y, int64_t B, int64_t T, int64_t out_stride, int32_t frame,
                          void* cuda_stream) {
     if (B < 0 || T < 0) return AEC_EINVAL;
-    if (frame != 512) return frame == 1024 ? AEC_EUNSUPPORTED : AEC_EINVAL;
-    if (T >= 1 && out_stride < (T - 1) * 256) return AEC_EINVAL;
+    if (frame != 512 && frame != 1024) return AEC_EINVAL;
+    if (T >= 1 && out_stride < (T - 1) * (frame / 2)) return AEC_EINVAL;
     if (B == 0 || T <= 1) return AEC_OK;
     if (!spec || !y || B > 65535) return AEC_EINVAL;
     Tables tab;
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
+    if (frame == 1024) {
+        const size_t smem1k = 4 * kFP1k * sizeof(float2) + (size_t)2 * kK1k * kPitch * sizeof(float) +
+                              (size_t)kTT * 512 * sizeof(float2);
+        rc = set_smem(istft1024_kernel, smem1k);
+        if (rc != AEC_OK) return rc;
+        dim3 grid1k((unsigned)((T - 1 + kTT - 2) / (kTT - 1)), (unsigned)B);
+        istft1024_kernel<<<grid1k, kThreads, smem1k, static_cast<cudaStream_t>(cuda_stream)>>>(spec, y, T, out_stride, tab);
+        AEC_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        return AEC_OK;
+    }
     const size_t smem = 8 * kTilePitch * sizeof(float2) + (size_t)2 * kK * kPitch * sizeof(float);
     rc = set_smem(istft512_kernel, smem);
     if (rc != AEC_OK) return rc;

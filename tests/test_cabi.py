@@ -66,6 +66,7 @@ def test_argument_errors_do_not_need_a_gpu():
     bad = _lib.default_cfg(512, algo=7)
     assert run(f, f, f, None, None, None, 1, 8, 8, 8, C.byref(bad), None) == -1
     assert lib.aec_stft(f, f, 1, 8, 8, 300, None) == -1
+    assert lib.aec_features(f, f, f, f, 1, 8, 8, 1024, 32, 0.0, 0.0, None) == -2   # 257-bin ERB config only
     assert lib.aec_istft(f, f, 1, 5, 8, 512, None) == -1                                # out_stride too small
 
 

@@ -166,6 +166,15 @@ def test_stft_istft_match_reference_golden(golden, i):
         assert np.abs(y.cpu().numpy() - y_ref).max() < 5e-6
 
 
+def test_stft_istft_frame_1024_golden(golden):
+    s = A.ConvSTFT(1024, 512, 1024, "hann", "complex")(_cuda(golden["x1024"]))
+    assert tuple(s.shape) == golden["stft1024"].shape
+    assert np.abs(s.cpu().numpy() - golden["stft1024"]).max() < 1e-4
+    y = A.ConviSTFT(1024, 512, 1024, "hann", "complex")(_cuda(golden["stft1024"]))
+    assert tuple(y.shape) == golden["istft1024"].shape
+    assert np.abs(y.cpu().numpy() - golden["istft1024"]).max() < 5e-6
+
+
 def test_istft_free_spectrum_golden(golden):
     y = A.ConviSTFT(512, 256, 512, "hann", "complex")(_cuda(golden["spec_free"])).cpu().numpy()
     assert np.abs(y - golden["istft_free"]).max() < 5e-6
