@@ -1,0 +1,79 @@
+"""Device timing of the stand-alone operators against the reference's formulation run on the same GPU.
+
+The reference computes its STFT as a dense strided convolution with a [2K, 1, N] kernel
+(Stage2_lhm/scripts/network/attention_ccrn.py:8-25, 45-52) and its iSTFT as a transposed convolution
+(:82-101).  /root/reference is not on the GPU box, so the conv formulation is RESTATED here with torch
+(for timing only; parity is pinned separately by the golden vectors)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import acoustic_echo_cancellation_b200 as A  # noqa: E402
+
+
+def conv_kernels(n=512):
+    w = torch.hann_window(n, periodic=True, dtype=torch.float64)
+    basis = torch.fft.rfft(torch.eye(n, dtype=torch.float64))           # [n, K]
+    k = torch.cat([basis.real, basis.imag], 1).T                        # [2K, n]
+    inv = torch.linalg.pinv(k).T
+    return (k * w)[:, None, :].float().cuda(), (inv * w)[:, None, :].float().cuda(), w.float().cuda()
+
+
+def timeit(fn, n=10):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def main():
+    B, L, n, hop = 128, 160000, 512, 256
+    x = 0.1 * torch.randn(B, L, device="cuda")
+    y = 0.1 * torch.randn(B, L, device="cuda")
+    kf, ki, w = conv_kernels(n)
+    stft, istft = A.ConvSTFT(n, hop, n, "hann", "complex"), A.ConviSTFT(n, hop, n, "hann", "complex")
+    erb = torch.from_numpy(A.erb_filterbank()).float().cuda()
+
+    def ref_stft(v):
+        return F.conv1d(F.pad(v[:, None, :], [n - hop, n - hop]), kf, stride=hop)
+
+    def ref_istft(s):
+        o = F.conv_transpose1d(s, ki, stride=hop)
+        t = (w[None, :, None] ** 2).repeat(1, 1, s.size(-1))
+        coff = F.conv_transpose1d(t, torch.eye(n, device="cuda")[:, None, :], stride=hop)
+        return (o / (coff + 1e-8))[..., n - hop:-(n - hop)]
+
+    def ref_feat(m, r):
+        out = []
+        for v in (m, r):
+            s = ref_stft(v)
+            mag = torch.sqrt(s[:, :257] ** 2 + s[:, 257:] ** 2 + 1e-9).transpose(1, 2)
+            out.append(mag @ erb)
+        return torch.cat([out[0], (out[0] - out[1]).abs()], 2)
+
+    s_ours = stft(x)
+    res = {
+        "shape": [B, L],
+        "stft_ms": {"ours": timeit(lambda: stft(x)), "conv_formulation": timeit(lambda: ref_stft(x))},
+        "istft_ms": {"ours": timeit(lambda: istft(s_ours)), "conv_formulation": timeit(lambda: ref_istft(s_ours))},
+        "features_ms": {"ours": timeit(lambda: A.stage2_features(x, y, erb, in_norm=False)),
+                        "conv_formulation": timeit(lambda: ref_feat(x, y))},
+        "max_abs_diff": {"stft": float((s_ours - ref_stft(x)).abs().max()),
+                         "istft": float((istft(s_ours) - ref_istft(s_ours)).abs().max()),
+                         "features": float((A.stage2_features(x, y, erb, in_norm=False) - ref_feat(x, y)).abs().max())},
+    }
+    print(json.dumps(res, indent=1))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/ops_bench.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
