@@ -5,6 +5,8 @@
 // All three reuse the half-warp FFT-256 of the fused stage-1 kernel; a CTA works on a tile of
 // 16 frames so the reference's [B, 2K, T] (T innermost) layout is read / written in 64-byte
 // runs through a shared-memory transpose.
+#include <cstdint>
+
 #include "aec_common.cuh"
 #include "fft_warp.cuh"
 
@@ -38,13 +40,26 @@ __device__ __forceinline__ void pack_pair_s(float2 ek, float2 em, float2 w, floa
 __device__ __forceinline__ void analyse_frame(const float* __restrict__ x, long long L, long long t, float shift,
                                               float2* tile, const Tables& tab, int h) {
     float2 v[16];
+    const long long base = (t - 1) * 256;
+    // interior frames of 8-byte aligned rows: unpredicated 64-bit loads (the common case)
+    const bool fast = t >= 1 && base + 512 <= L && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+    if (fast) {
+        const float2* xp = reinterpret_cast<const float2*>(x + base) + h;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const long long s = (t - 1) * 256 + 2 * h + 32 * j;
-        const float2 w = __ldg(&tab.win_a[h + 16 * j]);
-        const float x0 = (s >= 0 && s < L) ? __ldg(x + s) - shift : 0.f;
-        const float x1 = (s + 1 >= 0 && s + 1 < L) ? __ldg(x + s + 1) - shift : 0.f;
-        v[j] = make_float2(x0 * w.x, x1 * w.y);
+        for (int j = 0; j < 16; ++j) {
+            const float2 w = __ldg(&tab.win_a[h + 16 * j]);
+            const float2 xv = __ldg(xp + 16 * j);
+            v[j] = make_float2((xv.x - shift) * w.x, (xv.y - shift) * w.y);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const long long s = base + 2 * h + 32 * j;
+            const float2 w = __ldg(&tab.win_a[h + 16 * j]);
+            const float x0 = (s >= 0 && s < L) ? __ldg(x + s) - shift : 0.f;
+            const float x1 = (s + 1 >= 0 && s + 1 < L) ? __ldg(x + s + 1) - shift : 0.f;
+            v[j] = make_float2(x0 * w.x, x1 * w.y);
+        }
     }
     __syncwarp();
     fft256_halfwarp<false>(v, tile, tab.tw256, h);
@@ -174,67 +189,103 @@ __global__ void __launch_bounds__(kThreads) istft512_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------
-// Stage-2 feature front end: feat [B][T][2*bands]
+// Stage-2 feature front end: feat [B][T][2*bands]   (Stage2_lhm/scripts/network/ERB.py:262-290)
+//
+// A CTA walks tiles of 16 frames of one utterance.  Per tile: (1) a warp transforms one frame at a
+// time, lanes 0-15 the microphone and 16-31 the reference signal (same half-warp FFT as the stage-1
+// kernel), and stores the magnitudes; (2) the ERB projection runs with lane = (signal, frame) and the
+// band warp-uniform, looping only over the band's non-zero bin range [lo_b, hi_b) -- the bank is ~2
+// non-zeros per bin, so this is ~16x less work than the dense [T,257] @ [257,32] product the
+// reference does -- and (3) the [16][2*bands] tile is written out coalesced.  The bank and its
+// non-zero ranges are staged in shared memory once per CTA.
 // ---------------------------------------------------------------------------------------
+constexpr int kFeatMP = 259;   // magnitude row pitch (odd: lanes = frames read one bin conflict-free)
+
 __global__ void __launch_bounds__(kThreads) features512_kernel(const float* __restrict__ mic,
                                                                const float* __restrict__ ref,
                                                                const float* __restrict__ erb, float* __restrict__ feat,
                                                                long long L, long long in_stride, long long T, int bands,
                                                                float shift_mic, float shift_ref, Tables tab) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int kMP = 260;   // magnitude row pitch
-    float2* tiles = reinterpret_cast<float2*>(smem);                             // [8][256]
-    float* mag = reinterpret_cast<float*>(smem + 8 * kTilePitch * sizeof(float2));         // [2][kTT][kMP]
-    float* erbs = mag + 2 * kTT * kMP;                                           // [257][bands]
-    const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
-    const long long b = blockIdx.y, t0 = (long long)blockIdx.x * kTT;
-    for (int idx = tid; idx < kK * bands; idx += kThreads) erbs[idx] = __ldg(erb + idx);
-    float2* tile = tiles + hw * kTilePitch;
-    for (int sig = 0; sig < 2; ++sig) {
-        const float* xb = (sig == 0 ? mic : ref) + b * in_stride;
-        const float shift = sig == 0 ? shift_mic : shift_ref;
-        for (int i = 0; i < 2; ++i) {
-            const int tt = hw + 8 * i;
+    float2* tiles = reinterpret_cast<float2*>(smem);                                  // [8][kTilePitch]
+    float* mag = reinterpret_cast<float*>(smem + 8 * kTilePitch * sizeof(float2));    // [2][kTT][kFeatMP]
+    float* erbs = mag + 2 * kTT * kFeatMP;                                            // [257][bands]
+    float* outt = erbs + kK * bands;                                                  // [kTT][2*bands]
+    int* lo = reinterpret_cast<int*>(outt + kTT * 2 * bands);                         // [bands]
+    int* hi = lo + bands;                                                             // [bands]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, h = lane & 15;
+    const long long b = blockIdx.y;
+    const long long n_tiles = (T + kTT - 1) / kTT;
+
+    for (int i = tid; i < bands; i += kThreads) {
+        lo[i] = kK;
+        hi[i] = 0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kK * bands; idx += kThreads) {
+        const float e = __ldg(erb + idx);
+        erbs[idx] = e;
+        if (e != 0.f) {
+            atomicMin(&lo[idx % bands], idx / bands);
+            atomicMax(&hi[idx % bands], idx / bands + 1);
+        }
+    }
+    const float* xb = (half == 0 ? mic : ref) + b * in_stride;
+    const float shift = half == 0 ? shift_mic : shift_ref;
+    float2* tile = tiles + (2 * warp + half) * kTilePitch;
+    float* fb = feat + b * T * (2 * bands);
+
+    for (long long tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x) {
+        const long long t0 = tile_i * kTT;
+        __syncthreads();                       // previous tile's projection / copy-out finished
+        // ---- (1) analysis + magnitudes: warp w takes frames w, w+4, w+8, w+12 ----
+        for (int i = 0; i < kTT / 4; ++i) {
+            const int tt = warp + 4 * i;
             const long long t = t0 + tt;
-            float* mrow = mag + (sig * kTT + tt) * kMP;
-            {
-                analyse_frame(xb, t < T ? L : 0, t, shift, tile, tab, h);
+            analyse_frame(xb, t < T ? L : 0, t, shift, tile, tab, h);
+            float* mrow = mag + (half * kTT + tt) * kFeatMP;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int k = h + 16 * q;
-                    float2 xk, xm;
-                    unpack_pair_s(tile[k], tile[(256 - k) & 255], __ldg(&tab.tw512[k]), xk, xm);
-                    if (k == 0) {
-                        xk.y = 0.f;
-                        xm.y = 0.f;
-                    }
-                    mrow[k] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));        // ERB.py:277-278
-                    mrow[256 - k] = sqrtf(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
+            for (int q = 0; q < 8; ++q) {
+                const int k = h + 16 * q;
+                float2 xk, xm;
+                unpack_pair_s(tile[k], tile[(256 - k) & 255], __ldg(&tab.tw512[k]), xk, xm);
+                if (k == 0) {
+                    xk.y = 0.f;
+                    xm.y = 0.f;
                 }
-                if (h == 0) {
-                    float2 xk, xm;
-                    unpack_pair_s(tile[128], tile[128], make_float2(0.f, -1.f), xk, xm);
-                    mrow[128] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
+                mrow[k] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));        // ERB.py:277-278
+                mrow[256 - k] = sqrtf(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
+            }
+            if (h == 0) {
+                float2 xk, xm;
+                unpack_pair_s(tile[128], tile[128], make_float2(0.f, -1.f), xk, xm);
+                mrow[128] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- (2) ERB projection: lane = (signal, frame), band uniform per warp ----
+        {
+            const float* mrow = mag + lane * kFeatMP;      // lane = half*16 + frame  ==  (sig*kTT + tt)
+            for (int band = warp; band < bands; band += 4) {
+                const int k0 = lo[band], k1 = hi[band];
+                float acc = 0.f;
+                for (int k = k0; k < k1; ++k) acc = fmaf(mrow[k], erbs[k * bands + band], acc);   // ERB.py:282-283
+                // mic projection in lanes 0-15, ref projection in lanes 16-31 of the same frame
+                const float other = __shfl_xor_sync(0xffffffffu, acc, 16);
+                if (half == 0) {
+                    outt[h * 2 * bands + band] = acc;
+                    outt[h * 2 * bands + bands + band] = fabsf(acc - other);              // ERB.py:287-290
                 }
             }
         }
-    }
-    __syncthreads();
-    float* fb = feat + b * T * (2 * bands);
-    for (int idx = tid; idx < kTT * bands; idx += kThreads) {
-        const int tt = idx / bands, band = idx % bands;
-        if (t0 + tt >= T) continue;
-        const float* m0 = mag + (0 * kTT + tt) * kMP;
-        const float* m1 = mag + (1 * kTT + tt) * kMP;
-        float am = 0.f, ar = 0.f;
-        for (int k = 0; k < kK; ++k) {
-            const float e = erbs[k * bands + band];
-            am = fmaf(m0[k], e, am);                                                    // ERB.py:282
-            ar = fmaf(m1[k], e, ar);                                                    // ERB.py:283
+        __syncthreads();
+        // ---- (3) coalesced copy-out ----
+        const int row_len = 2 * bands;
+        for (int idx = tid; idx < kTT * row_len; idx += kThreads) {
+            const int tt = idx / row_len;
+            if (t0 + tt < T) fb[(t0 + tt) * row_len + (idx - tt * row_len)] = outt[idx];
         }
-        float* dst = fb + (t0 + tt) * (2 * bands);
-        dst[band] = am;
-        dst[bands + band] = fabsf(am - ar);                                             // ERB.py:287-290
     }
 }
 
@@ -460,10 +511,18 @@ extern "C" int aec_features(const float* mic, const float* ref, const float* erb
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
     const long long T = aec_num_frames(L, frame);
-    const size_t smem = 8 * kTilePitch * sizeof(float2) + (size_t)2 * kTT * 260 * sizeof(float) + (size_t)kK * bands * sizeof(float);
+    const size_t smem = 8 * kTilePitch * sizeof(float2) + (size_t)2 * kTT * kFeatMP * sizeof(float) +
+                        (size_t)kK * bands * sizeof(float) + (size_t)kTT * 2 * bands * sizeof(float) +
+                        (size_t)2 * bands * sizeof(int);
     rc = set_smem(features512_kernel, smem);
     if (rc != AEC_OK) return rc;
-    dim3 grid((unsigned)((T + kTT - 1) / kTT), (unsigned)B);
+    // a CTA walks several tiles so that the ERB bank is staged once per CTA, not once per tile
+    const long long n_tiles = (T + kTT - 1) / kTT;
+    long long per_utt = n_tiles;
+    if (B >= 512) per_utt = 2; else if (B >= 64) per_utt = 8;
+    if (per_utt > n_tiles) per_utt = n_tiles;
+    if (per_utt < 1) per_utt = 1;
+    dim3 grid((unsigned)per_utt, (unsigned)B);
     features512_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
         mic, ref, erb, feat, L, in_stride, T, bands, shift_mic, shift_ref, tab);
     AEC_CUDA_CHECK(cudaGetLastError());
