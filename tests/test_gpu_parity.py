@@ -115,6 +115,42 @@ def test_unaligned_rows_take_the_in_kernel_slow_path():
     assert float(bo[:, 0].abs().max()) == 0 and float(bo[:, L + 1:].abs().max()) == 0   # no stray writes
 
 
+@pytest.mark.parametrize("frame,P,algo,echo", [(512, 4, 0, False), (512, 4, 1, True), (512, 8, 1, False),
+                                               (512, 16, 1, True), (512, 16, 0, False), (1024, 8, 0, True)])
+def test_no_stray_writes_and_run_to_run_determinism(frame, P, algo, echo):
+    """compute-sanitizer is closed on this pool: canaries around every output row and bitwise
+    run-to-run equality (a data race would show as a flaky difference) stand in for it."""
+    B, L, pad = 5, 9000, 64
+    hop = frame // 2
+    g = torch.Generator(device="cuda").manual_seed(3)
+    far = 0.1 * torch.randn(B, L, device="cuda", generator=g)
+    mic = 0.5 * torch.roll(far, 11, dims=1) + 0.01 * torch.randn(B, L, device="cuda", generator=g)
+    ns = torch.tensor([L, L - 1, L - hop - 3, 17, L // 2], device="cuda")
+    cfg = A.Stage1Config(frame=frame, partitions=P, algo=algo, erle_skip_hops=2)
+    canary = 12345.0
+    stride = L + 2 * pad
+    stride += (-stride) % 4
+    outs = []
+    for _ in range(2):
+        buf = torch.full((B, stride), canary, device="cuda")
+        ebuf = torch.full((B, stride), canary, device="cuda")
+        lib = _lib.load()
+        c = cfg.to_c()
+        erle = torch.full((B + 2,), canary, device="cuda")
+        rc = lib.aec_stage1_run(far.data_ptr(), mic.data_ptr(), buf[:, pad:].data_ptr(),
+                                ebuf[:, pad:].data_ptr() if echo else None, erle[1:].data_ptr(), ns.data_ptr(),
+                                B, L, L, stride, C.byref(c), int(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        torch.cuda.synchronize()
+        for t in ((buf, ebuf) if echo else (buf,)):
+            assert bool((t[:, :pad] == canary).all()) and bool((t[:, pad + L:] == canary).all())
+            assert bool(torch.isfinite(t[:, pad:pad + L]).all())
+        assert float(erle[0]) == canary and float(erle[-1]) == canary
+        outs.append((buf.clone(), ebuf.clone(), erle.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
 def test_host_buffer_entry_matches_device_entry():
     L, B = 16000, 10
     d = synth.make_batch(0, B, L)
