@@ -10,9 +10,10 @@ from ._lib import ALGO_KALMAN, ALGO_NLMS, AecError, LIB_PATH  # noqa: F401
 from .stage1 import (HostPipeline, Stage1Config, fp32_peak_tflops, launch_count, num_frames,  # noqa: F401
                      out_samples, pinned_empty, stage1_aec)
 from .spectral import ConvSTFT, ConviSTFT, erb_filterbank, stage2_features  # noqa: F401
+from .stage2 import LittleNetInference  # noqa: F401
 
 __all__ = [
     "ALGO_KALMAN", "ALGO_NLMS", "AecError", "LIB_PATH", "HostPipeline", "Stage1Config", "fp32_peak_tflops",
     "launch_count", "num_frames", "out_samples", "pinned_empty", "stage1_aec", "ConvSTFT", "ConviSTFT",
-    "erb_filterbank", "stage2_features",
+    "erb_filterbank", "stage2_features", "LittleNetInference",
 ]

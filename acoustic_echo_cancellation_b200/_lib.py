@@ -43,6 +43,13 @@ class AecError(RuntimeError):
         super().__init__(what)
 
 
+class Stage2Weights(C.Structure):
+    """Mirror of ``struct aec_stage2_weights`` (device pointers to Little_net's state_dict tensors)."""
+
+    _fields_ = [(n, C.c_void_p) for n in ("gru_w_ih", "gru_w_hh", "gru_b_ih", "gru_b_hh", "lin1_w", "lin1_b",
+                                           "lin2_w", "lin2_b")]
+
+
 # every symbol include/aec_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _I64 = C.c_int64
@@ -64,6 +71,8 @@ SIGNATURES = {
     "aec_stft": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P]),
     "aec_istft": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P]),
     "aec_features": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I32, C.c_float, C.c_float, _P]),
+    "aec_stage2_mask": (C.c_int, [_P, C.POINTER(Stage2Weights), _P, _I64, _I64, _I32, _P]),
+    "aec_stage2_synth": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I32, _I32, C.c_float, _P]),
     "aec_bench_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), _P]),
     "aec_launch_count": (_I64, [C.c_int]),
 }

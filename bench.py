@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
     if args.impl == "reference":
@@ -240,6 +241,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: acoustic_echo_cancellation_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_cpus = None
+    if world > 1 and not args.no_numa_bind:
+        from acoustic_echo_cancellation_b200 import hostutil
+        numa_cpus = hostutil.bind_to_gpu_numa(local)     # host buffers of the e2e leg land GPU-local
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -415,7 +420,8 @@ def main():
         "config": {"workload": wl["name"], "utterances_per_gpu": B, "samples": L, "sample_rate": SR,
                    "frame": FRAME, "hop": HOP, "partitions": P, "algo": "nlms" if algo == 0 else "kalman",
                    "l2": "inputs %.1f GB/GPU per step >> 126 MB L2 (no flush needed)" % (2 * B * L * 4 / 1e9),
-                   "parallelism": f"utterance-sharded x{world}, metrics-only all_gather"},
+                   "parallelism": f"utterance-sharded x{world}, metrics-only all_gather",
+                   "host_cpus_rank0": (f"{len(numa_cpus)} GPU-local CPUs" if numa_cpus else "unbound")},
         "per_gpu": value / world,
         "e2e": e2e, "e2e_bitwise_equal_to_device_path": e2e_match,
         "gpu_launches": int(launches),

@@ -133,6 +133,30 @@ int aec_features(const float* mic, const float* ref, const float* erb, float* fe
                  int64_t in_stride, int32_t frame, int32_t bands, float shift_mic, float shift_ref,
                  void* cuda_stream);
 
+/* Stage-2 residual-echo suppressor inference (the consumer of the stage-1 output), for the
+ * reference's live model Little_net (Stage2_lhm/scripts/network/ERB.py:203-334, 32 ERB bands):
+ *   feat = aec_features(stage1_error or mic, far, erb)                          ERB.py:254-290
+ *   aec_stage2_mask : GRU(64->32) + Linear(64->32)+ReLU + Linear(32->32)+sigmoid, est_erb = mask*mic_erb
+ *                     feat [B][T][64] -> est_erb [B][T][32]                       ERB.py:293-304
+ *   aec_stage2_synth: out = iSTFT((est_erb @ erb^T) * STFT(mic - shift_mic)) + 1e-9 -> out [B][out_stride]
+ *                                                                                 ERB.py:306-316
+ * Weights are the module's state_dict tensors (row-major, PyTorch layouts, gate order r,z,n), on the device. */
+typedef struct aec_stage2_weights {
+    const float* gru_w_ih; /* gru1.weight_ih_l0 [96][64] */
+    const float* gru_w_hh; /* gru1.weight_hh_l0 [96][32] */
+    const float* gru_b_ih; /* gru1.bias_ih_l0   [96]     */
+    const float* gru_b_hh; /* gru1.bias_hh_l0   [96]     */
+    const float* lin1_w;   /* linear1.weight    [32][64] */
+    const float* lin1_b;   /* linear1.bias      [32]     */
+    const float* lin2_w;   /* linear2.weight    [32][32] */
+    const float* lin2_b;   /* linear2.bias      [32]     */
+} aec_stage2_weights;
+int aec_stage2_mask(const float* feat, const aec_stage2_weights* w, float* est_erb, int64_t B, int64_t T,
+                    int32_t bands, void* cuda_stream);
+int aec_stage2_synth(const float* mic, const float* est_erb, const float* erb, float* out, int64_t B, int64_t L,
+                     int64_t in_stride, int64_t out_stride, int32_t frame, int32_t bands, float shift_mic,
+                     void* cuda_stream);
+
 /* Measurement helpers used by bench.py (not part of the reference-facing surface).
  * aec_bench_fp32_peak: dependent-free FFMA loop on every SM; returns achieved FP32 TFLOP/s. */
 int aec_bench_fp32_peak(int iters, double* tflops, void* cuda_stream);

@@ -7,7 +7,7 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 Parity status
 ---------------------------------------------------
 * ``stft`` / ``istft`` / ``count_frames_reference`` / ``erb_filterbank`` /
-  ``stage2_features`` restate code that EXISTS in the reference and are pinned
+  ``stage2_features`` / ``stage2_little_net`` restate code that EXISTS in the reference and are pinned
   by golden vectors produced by importing the reference modules
   (``tests/golden/make_golden.py``):
     - STFT analysis      Stage2_lhm/scripts/network/attention_ccrn.py:8-25,45-52
@@ -355,6 +355,47 @@ def stage2_features(mic: np.ndarray, ref: np.ndarray, erb: np.ndarray,
         out.append(mag.astype(dtype) @ erb)
     mic_erb, ref_erb = out
     return np.concatenate([mic_erb, np.abs(mic_erb - ref_erb)], axis=2)
+
+
+def stage2_little_net(mic: np.ndarray, ref: np.ndarray, erb: np.ndarray, w: dict,
+                      frame: int = WIN_SIZE, hop: int = HOP_SIZE, dtype=np.float64) -> np.ndarray:
+    """Inference path of the reference's live Stage-2 model ``Little_net.forward``
+    (network/ERB.py:252-316; pinned by tests/golden/reference_stage2.npz, produced by running the
+    reference module itself).  ``w`` holds the state_dict arrays ``gru1_weight_ih_l0`` [96,64],
+    ``gru1_weight_hh_l0`` [96,32], ``gru1_bias_ih_l0``, ``gru1_bias_hh_l0`` (PyTorch gate order r, z, n),
+    ``linear1_weight`` [32,64], ``linear1_bias``, ``linear2_weight`` [32,32], ``linear2_bias``.
+    Returns ``out_wav`` [B, (T-1)*hop]."""
+    mic = np.atleast_2d(np.asarray(mic, dtype=dtype))
+    ref = np.atleast_2d(np.asarray(ref, dtype=dtype))
+    erb = np.asarray(erb, dtype=dtype)
+    g = {k: np.asarray(v, dtype=dtype) for k, v in w.items()}
+    mic = mic - mic.mean() / mic.std(ddof=1)                               # ERB.py:254
+    ref = ref - ref.mean() / ref.std(ddof=1)                               # ERB.py:255
+    M = stft_complex(mic, frame, hop, dtype)                               # ERB.py:263
+    R = stft_complex(ref, frame, hop, dtype)                               # ERB.py:264
+    merb = np.sqrt(M.real ** 2 + M.imag ** 2 + 1e-9) @ erb                 # ERB.py:277, 282
+    rerb = np.sqrt(R.real ** 2 + R.imag ** 2 + 1e-9) @ erb                 # ERB.py:278, 283
+    x = np.concatenate([merb, np.abs(merb - rerb)], axis=2)                # ERB.py:287-290
+    B, T, _ = x.shape
+    nh = g["gru1_weight_hh_l0"].shape[1]
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))                               # noqa: E731
+    h = np.zeros((B, nh), dtype=dtype)
+    out1 = np.zeros((B, T, nh), dtype=dtype)
+    for t in range(T):                                                     # ERB.py:293 (torch.nn.GRU cell)
+        gi = x[:, t] @ g["gru1_weight_ih_l0"].T + g["gru1_bias_ih_l0"]
+        gh = h @ g["gru1_weight_hh_l0"].T + g["gru1_bias_hh_l0"]
+        r = sig(gi[:, :nh] + gh[:, :nh])
+        z = sig(gi[:, nh:2 * nh] + gh[:, nh:2 * nh])
+        n = np.tanh(gi[:, 2 * nh:] + r * gh[:, 2 * nh:])
+        h = (1.0 - z) * n + z * h
+        out1[:, t] = h
+    outcat = np.concatenate([out1, merb], axis=2)                          # ERB.py:295
+    out2 = np.maximum(outcat @ g["linear1_weight"].T + g["linear1_bias"], 0.0)   # ERB.py:298
+    mask = sig(out2 @ g["linear2_weight"].T + g["linear2_bias"])           # ERB.py:301
+    est_erb = mask * merb                                                  # ERB.py:304
+    gain = est_erb @ erb.T                                                 # ERB.py:306-307
+    est = gain * M                                                         # ERB.py:309-310
+    return istft_complex(est, frame, hop, dtype) + dtype(1e-9)             # ERB.py:315-316
 
 
 # --------------------------------------------------------------------------------------

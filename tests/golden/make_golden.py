@@ -104,5 +104,37 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
 
 
+def stage2_golden():
+    """Little_net inference (Stage2_lhm/scripts/network/ERB.py:203-334) with seeded random weights:
+    the reference module itself is run on CPU; weights, inputs and `out_wav` go to
+    tests/golden/reference_stage2.npz."""
+    from network.ERB import Little_net
+
+    torch.manual_seed(1234)
+    conf = {"win_size": 512, "hop_size": 256}
+    net = Little_net(conf, 32).eval()
+    with torch.no_grad():
+        for p_ in net.parameters():            # lively, well-conditioned random weights
+            p_.copy_(0.3 * torch.randn_like(p_))
+    rng = np.random.default_rng(777)
+    mic = (0.2 * rng.standard_normal((3, 6144)) + 0.01).astype(np.float32)
+    ref = (0.2 * rng.standard_normal((3, 6144)) - 0.02).astype(np.float32)
+    near = (0.1 * rng.standard_normal((3, 6144))).astype(np.float32)
+    erb = EquivalentRectangularBandwidth(257, 16000, 32, 0, 8000).filters
+    with torch.no_grad():
+        out_wav, loss = net(torch.from_numpy(mic), torch.from_numpy(ref), torch.from_numpy(near),
+                            torch.from_numpy(erb).float())
+    out = {"mic": mic, "ref": ref, "erb": erb.astype(np.float32), "out_wav": out_wav.numpy()}
+    for k, v in net.state_dict().items():
+        if k.startswith(("gru1.", "linear1.", "linear2.")):
+            out["w_" + k.replace(".", "_")] = v.numpy()
+    path = os.path.join(HERE, "reference_stage2.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", sorted(out))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "stage2":
+        stage2_golden()
+    else:
+        main()

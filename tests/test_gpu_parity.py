@@ -223,6 +223,19 @@ def test_feature_front_end_golden(golden):
     assert np.abs(f - golden["feat"]).max() < 2e-4 * np.abs(golden["feat"]).max()
 
 
+def test_stage2_little_net_inference_matches_reference_module():
+    """Stage-2 inference (ERB.py:252-316) against the output of the reference module itself."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_stage2.npz"))
+    w = {k[2:]: g[k] for k in g.files if k.startswith("w_")}
+    net = A.LittleNetInference(w, g["erb"])
+    out = net(_cuda(g["mic"]), _cuda(g["ref"])).cpu().numpy()
+    assert out.shape == g["out_wav"].shape
+    assert np.abs(out - g["out_wav"]).max() < 2e-4 * np.abs(g["out_wav"]).max()
+    ref64 = O.stage2_little_net(g["mic"], g["ref"], g["erb"], w)
+    assert np.abs(out - ref64).max() < 2e-4 * np.abs(ref64).max()
+
+
 def test_stft_3d_input_and_ctor_errors():
     x = torch.randn(2, 1, 2048, device="cuda")
     s = A.ConvSTFT(512, 256, 512, "hann", "complex")(x)

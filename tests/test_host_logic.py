@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from acoustic_echo_cancellation_b200 import sharding, wav2h5
+from acoustic_echo_cancellation_b200 import hostutil, sharding, wav2h5
 
 
 def test_shard_range_partitions_exactly():
@@ -134,3 +134,10 @@ def test_cli_flags_match_the_reference():
         "../examples/filelists", 16000)
     b = wav2h5.build_parser("test").parse_args(["--val_path", "x", "--sr", "8000"])
     assert b.val_path == "x" and b.sr == 8000
+
+
+def test_cpulist_parser_and_bind_is_harmless_without_gpu():
+    assert hostutil._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert hostutil._parse_cpulist("") == []
+    if not torch.cuda.is_available():
+        assert hostutil.gpu_local_cpus(0) is None and hostutil.bind_to_gpu_numa(0) is None

@@ -54,3 +54,12 @@ def test_feature_front_end(golden):
     ref = golden["feat"]
     assert f.shape == ref.shape
     assert np.abs(f - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_stage2_little_net_inference_matches_reference_module():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_stage2.npz"))
+    w = {k[2:]: g[k] for k in g.files if k.startswith("w_")}
+    out = O.stage2_little_net(g["mic"], g["ref"], g["erb"], w)
+    assert out.shape == g["out_wav"].shape
+    assert np.abs(out - g["out_wav"]).max() < 2e-4 * max(1.0, np.abs(g["out_wav"]).max())
