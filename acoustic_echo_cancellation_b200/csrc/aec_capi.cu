@@ -261,6 +261,12 @@ static int validate_cfg(const aec_cfg* cfg) {
     return AEC_OK;
 }
 
+#ifdef AEC_PHASE_TIMING
+// developer build only (tools/phase_timing.py): device buffer [B][NW][12] of per-phase cycle counts
+static long long* g_phase_buffer = nullptr;
+extern "C" void aec_debug_set_phase_buffer(void* p) { g_phase_buffer = static_cast<long long*>(p); }
+#endif
+
 extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, float* echo_est, float* erle_db,
                               const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride, int64_t out_stride,
                               const aec_cfg* cfg, void* cuda_stream) {
@@ -296,6 +302,9 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
     p.kc0 = cfg->kalman_c0;
     p.keps = cfg->kalman_eps;
     p.erle_skip_hops = cfg->erle_skip_hops;
+#ifdef AEC_PHASE_TIMING
+    p.dbg = g_phase_buffer;
+#endif
     auto aligned = [](const void* ptr, size_t a) { return (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) == 0; };
     p.use_tma = (aligned(far, 16) && aligned(mic, 16) && (in_stride % 4) == 0) ? 1 : 0;
     p.vec_out = (aligned(err, 8) && (!echo_est || aligned(echo_est, 8)) && (out_stride % 2) == 0) ? 1 : 0;

@@ -49,7 +49,25 @@ struct Stage1Params {
     const float2* tw512;   // [129]     exp(-2 pi i k / 512)
     const float2* win_a;   // [256]     0.5 * hann[2m], 0.5 * hann[2m+1]
     const float2* win_s;   // [256]     hann[n] / (512 * (coff[n] + 1e-8)), n = 2m, 2m+1
+#ifdef AEC_PHASE_TIMING
+    long long* dbg;        // developer build only: [B][NW][12] cycles per phase (tools/phase_timing.py)
+#endif
 };
+
+// Developer instrumentation (compiled out of the product library): lane 0 of every warp accumulates
+// the cycles between consecutive AEC_TICK points in shared memory.
+#ifdef AEC_PHASE_TIMING
+#define AEC_TICK(i)                                                   \
+    do {                                                              \
+        if (lane == 0) {                                              \
+            const long long now_ = clock64();                         \
+            dbg_sm[warp][i] += now_ - dbg_sm[warp][11];               \
+            dbg_sm[warp][11] = now_;                                  \
+        }                                                             \
+    } while (0)
+#else
+#define AEC_TICK(i) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------
 // mbarrier / bulk-copy (TMA) wrappers
@@ -90,6 +108,18 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
             smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+// one lane of a converged warp (SASS: ELECT); keeps the bulk-copy operands in uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void st_stream_f2(float* p, float2 v) {
     asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
@@ -278,22 +308,36 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
 
     long long n_ll = prm.n_samples ? prm.n_samples[b] : prm.L;
     n_ll = n_ll < 0 ? 0 : (n_ll > prm.L ? prm.L : n_ll);
-    const int n = static_cast<int>(n_ll);
-    const int T = n / 256 + 1;               // frames (attention_ccrn.py:48-49 with N = 2H)
-    const int n_chunks = (T + F - 1) / F;
+    const int T = static_cast<int>(n_ll) / 256 + 1;               // frames (attention_ccrn.py:48-49 with N = 2H)
     // Row pointers are recomputed where they are used (a handful of integer instructions per chunk)
     // instead of living in registers across the FFT phases, where the compiler would spill them:
     // with the 228 KB shared-memory carve-out there is no L1, so a spill reload costs an L2 round trip.
     auto row_off = [&](long long stride) {
-        long long v = b * stride;
-        asm volatile("" : "+l"(v));          // opaque: not hoisted out of the chunk loop
-        return v;
+        unsigned bx;
+        asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));   // re-read where used: nothing hoisted, nothing spilled
+        return static_cast<long long>(bx) * stride;
     };
 
+    // Owner of the self-mirrored bin 128 (the 257th bin on 256 bin slots; its serial pass costs one warp
+    // ~70 instructions per frame).  Warp w of a two-warp utterance always sits on scheduler (slot + w) % 4
+    // of its SM, so a fixed owner loads one scheduler of each pair more than the other for every resident
+    // utterance at once.  Alternate the owner with the hardware warp slot: co-resident utterances on the
+    // same scheduler pair then put the extra pass on different schedulers.
+    int* mid_owner = reinterpret_cast<int*>(mbar + 1);
     if (tid == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
+        unsigned hw_warp;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
+        *mid_owner = (NW == 2) ? static_cast<int>((hw_warp >> 2) & 1u) : NW - 1;
     }
+#ifdef AEC_PHASE_TIMING
+    __shared__ long long dbg_sm[NW][12];
+    if (lane == 0) {
+        for (int i = 0; i < 11; ++i) dbg_sm[warp][i] = 0;
+        dbg_sm[warp][11] = clock64();
+    }
+#endif
     // Utterances resident on one SM start together and would otherwise run their FADD-heavy FFT
     // phases and FFMA-heavy filter phases in lock-step; skew them by a fraction of a chunk.
     if (prm.stagger_ns > 0) {
@@ -309,6 +353,34 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         const long long in_off = row_off(prm.in_stride);
         const float* far_b = prm.far + in_off;
         const float* mic_b = prm.mic + in_off;
+        // Interior chunk (every hop of the range lies inside the signal, rows 16-byte aligned): the hops
+        // are contiguous in HBM and contiguous in the ring up to its wrap-around, so the whole range is
+        // one or two bulk copies per signal instead of one per hop (the per-hop issue loop used to cost
+        // the producing warp ~60 instructions per frame on the critical path of the filter phase).
+        if (prm.use_tma && b0 >= 1 && b1 >= b0 && b1 <= T - 1) {   // b1 * 256 <= n
+            if (elect_one()) {
+                const int nb = b1 - b0 + 1;
+                const int s0 = b0 % R;
+                const int run1 = nb < R - s0 ? nb : R - s0;
+                const float* src_f = far_b + (b0 - 1) * 256;
+                const float* src_m = mic_b + (b0 - 1) * 256;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(mbar, static_cast<uint32_t>(nb) * 2048u);
+                tma_load_1d(stage + (0 * R + s0) * 256, src_f, static_cast<uint32_t>(run1) * 1024u, mbar);
+                tma_load_1d(stage + (1 * R + s0) * 256, src_m, static_cast<uint32_t>(run1) * 1024u, mbar);
+                if (run1 < nb) {
+                    const uint32_t rest = static_cast<uint32_t>(nb - run1) * 1024u;
+                    tma_load_1d(stage + (0 * R) * 256, src_f + run1 * 256, rest, mbar);
+                    tma_load_1d(stage + (1 * R) * 256, src_m + run1 * 256, rest, mbar);
+                }
+            }
+            return;
+        }
+        // (slow path, first chunk / ragged edge / unaligned rows only: the sample count is re-read here so
+        //  that it does not occupy a register across the whole chunk loop)
+        long long n_re = prm.n_samples ? prm.n_samples[blockIdx.x] : prm.L;
+        n_re = n_re < 0 ? 0 : (n_re > prm.L ? prm.L : n_re);
+        const int n = static_cast<int>(n_re);
         if (lane == 0) {
             int nt = 0;
             for (int beta = b0; beta <= b1; ++beta) nt += (prm.use_tma && beta >= 1 && beta * 256 <= n) ? 1 : 0;
@@ -398,13 +470,15 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     }
     const float2 w_mid = make_float2(0.f, -1.f);
 
-    float acc_mic = 0.f, acc_err = 0.f;      // ERLE energies (mic: lanes 16-31, err: lanes 0-15)
-    const bool want_erle = prm.erle_db != nullptr;
+    float acc_e = 0.f;     // ERLE energies in ONE register: lanes 16-31 accumulate the microphone, lanes 0-15 the error
 
-    for (int c = 0; c < n_chunks; ++c) {
+    // (chunk count not kept in a register: every use is a comparison of the frame index with T)
+    for (int c = 0; c * F < T; ++c) {
         const int t0 = c * F;
+        AEC_TICK(0);                         // loop tail / prologue
         __syncthreads();                     // manual-path staging stores of the producer visible
         mbar_wait(mbar, static_cast<uint32_t>(c & 1));
+        AEC_TICK(1);                         // barrier + staged-data wait
 
         // ================= phase A : analysis =================
 #pragma unroll 1
@@ -425,17 +499,20 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     if (j >= 8) e_acc = fmaf(x.x, x.x, fmaf(x.y, x.y, e_acc));
                 }
                 // second half of frame t is output hop t (block t+1): inside the ERLE span?
-                if (want_erle && half == 1 && t + 1 <= T - 1 && t >= prm.erle_skip_hops) acc_mic += e_acc;
+                if (prm.erle_db != nullptr && half == 1 && t + 1 <= T - 1 && t >= prm.erle_skip_hops) acc_e += e_acc;
                 float2* tile = zbuf + (tl * 2 + half) * kTilePitch;
                 fft256_halfwarp_regs<false>(v, tile, twr, h);
 #pragma unroll
                 for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
             }
         }
+        AEC_TICK(2);                         // phase A
         __syncthreads();
+        AEC_TICK(3);                         // barrier after A
 
         // stage the next chunk's hops while the filter and synthesis phases run
-        if (warp == 0 && c + 1 < n_chunks) produce(t0 + F + 1, t0 + 2 * F);
+        if (warp == 0 && t0 + F < T) produce(t0 + F + 1, t0 + 2 * F);
+        AEC_TICK(4);                         // produce
 
         // ================= phase B : per-bin recurrence =================
         // (frame loop deliberately NOT unrolled: the whole chunk loop must fit the 32 KB
@@ -494,7 +571,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     }
                 }
                 if constexpr (!kMidTapParallel) {
-                    if (tid == NT - 1) {     // self-mirrored bin 128, serial on the last thread
+                    // self-mirrored bin 128, serial on the last lane of the owning warp (owner re-read from shared
+                    // memory: a register live across the chunk loop tips the 128-register build into spilling)
+                    if (tid == *static_cast<volatile int*>(mid_owner) * 32 + 31) {
                         float2 xk, xm, yk, ym, ek, hk, gk, gm;
                         const float2 fa = zf[128], ma = zm[128];
                         unpack_pair(fa, fa, w_mid, xk, xm);
@@ -510,7 +589,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                             zm[128] = gk;
                         }
                     }
-                } else if (warp == NW - 1) {  // self-mirrored bin 128, one lane per tap
+                }
+                if constexpr (kMidTapParallel) if (warp == NW - 1) {  // self-mirrored bin 128, one lane per tap
                     // butterfly over the (power-of-two padded) tap lanes only: log2(P) steps
                     constexpr int kTapLanes = P <= 1 ? 1 : P <= 2 ? 2 : P <= 4 ? 4 : P <= 8 ? 8 : P <= 16 ? 16 : 32;
                     auto wsum = [](float v) {
@@ -562,7 +642,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                 }
             }
         }
+        AEC_TICK(5);                         // phase B
         __syncthreads();
+        AEC_TICK(6);                         // barrier after B
 
         // ================= phase C : synthesis + overlap-add =================
         const int tl = 2 * warp + half;      // this half-warp's frame inside the chunk
@@ -607,7 +689,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                         float* dst = out_b[sgn] + (long long)t * 256 + 2 * h + 32 * r;
                         if (prm.vec_out) st_stream_f2(dst, o);
                         else { st_stream_f1(dst, o.x); st_stream_f1(dst + 1, o.y); }
-                        if (sgn == 0 && t >= prm.erle_skip_hops) acc_err = fmaf(o.x, o.x, fmaf(o.y, o.y, acc_err));
+                        if (sgn == 0 && t >= prm.erle_skip_hops) acc_e = fmaf(o.x, o.x, fmaf(o.y, o.y, acc_e));
                     }
                 } else {
                     tail_dst[h + 16 * r] = u[8 + r];
@@ -617,7 +699,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                 head[sgn][r] = u[r];
             }
         }
+        AEC_TICK(7);                         // phase C (inverse FFT + in-warp overlap)
         __syncthreads();
+        AEC_TICK(8);                         // barrier after C
         // cross-warp overlap: block t (lower frame) = predecessor's tail + this frame's first half
         if (synth_warp && half == 0 && t >= 1 && t <= T - 1) {
 #pragma unroll
@@ -631,13 +715,13 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     float* dst = out_b[sgn] + (long long)(t - 1) * 256 + 2 * h + 32 * r;
                     if (prm.vec_out) st_stream_f2(dst, o);
                     else { st_stream_f1(dst, o.x); st_stream_f1(dst + 1, o.y); }
-                    if (sgn == 0 && t - 1 >= prm.erle_skip_hops) acc_err = fmaf(o.x, o.x, fmaf(o.y, o.y, acc_err));
+                    if (sgn == 0 && t - 1 >= prm.erle_skip_hops) acc_e = fmaf(o.x, o.x, fmaf(o.y, o.y, acc_e));
                 }
             }
         }
         // the last warp's tail crosses into the next chunk: warp 0 (which has just consumed the old
         // carry) moves it out of Zbuf before the next analysis phase overwrites the tile.
-        if (warp == 0 && c + 1 < n_chunks) {
+        if (warp == 0 && t0 + F < T) {
             __syncwarp();
 #pragma unroll
             for (int sgn = 0; sgn < NSIG; ++sgn) {
@@ -648,27 +732,31 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         }
     }
 
+#ifdef AEC_PHASE_TIMING
+    AEC_TICK(9);
+    if (lane == 0 && prm.dbg) {
+        unsigned hw_warp, hw_sm;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(hw_sm));
+        dbg_sm[warp][10] = (long long)hw_sm * 1000 + hw_warp;      // placement of this warp
+        for (int i = 0; i < 12; ++i) prm.dbg[((long long)blockIdx.x * NW + warp) * 12 + i] = dbg_sm[warp][i];
+    }
+#endif
     // ---- epilogue: zero the output beyond (T-1)*256, ERLE ------------------------------------
     {
         const long long valid = (long long)(T - 1) * 256;
-        float* out_b[2] = {prm.err + b * prm.out_stride, ECHO ? prm.echo + b * prm.out_stride : nullptr};
+        float* out_b[2] = {prm.err + row_off(prm.out_stride), ECHO ? prm.echo + row_off(prm.out_stride) : nullptr};
         for (long long i = valid + tid; i < prm.out_stride && i < prm.L; i += NT) {
             out_b[0][i] = 0.f;
             if constexpr (ECHO) out_b[1][i] = 0.f;
         }
     }
-    if (want_erle) {
+    if (prm.erle_db != nullptr) {
         __syncthreads();
         float* red = reinterpret_cast<float*>(zbuf);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc_mic += __shfl_xor_sync(0xffffffffu, acc_mic, o);
-            acc_err += __shfl_xor_sync(0xffffffffu, acc_err, o);
-        }
-        if (lane == 0) {
-            red[2 * warp] = acc_mic;
-            red[2 * warp + 1] = acc_err;
-        }
+        for (int o = 8; o > 0; o >>= 1) acc_e += __shfl_xor_sync(0xffffffffu, acc_e, o);   // within each half-warp
+        if (h == 0) red[2 * warp + (half ^ 1)] = acc_e;      // [2w] microphone (lane 16), [2w+1] error (lane 0)
         __syncthreads();
         if (tid == 0) {
             float pm = 0.f, pe = 0.f;
@@ -676,7 +764,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                 pm += red[2 * w];
                 pe += red[2 * w + 1];
             }
-            prm.erle_db[b] = 10.f * log10f(fmaxf(pm, 1e-20f) / fmaxf(pe, 1e-20f));
+            prm.erle_db[blockIdx.x] = 10.f * log10f(fmaxf(pm, 1e-20f) / fmaxf(pe, 1e-20f));
         }
     }
 }

@@ -27,9 +27,22 @@ inline cudaError_t launch_stage1_instance(const Stage1Params& prm, cudaStream_t 
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         // The kernel keeps its tables in shared memory / registers and does not need L1: ask for
-        // the largest carve-out so that 7 two-warp utterances (31.8 KB each) fit on one SM.
+        // the largest carve-out so that 7 two-warp utterances (31.8 KB each) fit on one SM ...
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
+        // ... but no larger than the resident utterances need: the long-filter kernels (2 utterances of
+        // 60-90 KB per SM) still spill a few registers at their 128-register cap, and what is left of
+        // the 256 KB array serves those reloads from L1 instead of L2.
+        int resident = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, NW * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (resident > 0) {
+            const size_t need = size_t(resident) * (smem + 1024);
+            int pct = static_cast<int>((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+            pct = pct > 100 ? 100 : pct;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            if (e != cudaSuccess) return e;
+        }
         configured_dev = dev;
     }
     kern<<<dim3((unsigned)prm.B), dim3(NW * 32), smem, s>>>(prm);
