@@ -359,27 +359,32 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 1, host buffers: double-buffered H2D -> kernel -> D2H pipeline
+// stage 1, host buffers: H2D -> kernel -> D2H pipeline, kSlots slices in flight
 // ------------------------------------------------------------------------------------------
+// Slices in flight.  Every slot is one stream running H2D -> kernel -> D2H for one slice; a slice of 64
+// utterances keeps the GPU busy for ~0.65 ms (the latency of one utterance) between copies of 0.75-1.5 ms
+// per direction, so two slots leave both DMA engines idle part of the time; four keep them saturated.
+constexpr int kSlots = 4;
+
 struct aec_host_ctx {
     int device = 0;
     int64_t slice = 0;       // utterances per slice
     int64_t max_samples = 0;
     int64_t stride = 0;      // device row stride (multiple of 4 floats)
-    cudaStream_t stream[2] = {nullptr, nullptr};
-    float* d_far[2] = {nullptr, nullptr};
-    float* d_mic[2] = {nullptr, nullptr};
-    float* d_err[2] = {nullptr, nullptr};
-    float* d_echo[2] = {nullptr, nullptr};
-    float* d_erle[2] = {nullptr, nullptr};
-    long long* d_n[2] = {nullptr, nullptr};
-    int16_t* d_pcm[2] = {nullptr, nullptr};   // [2 signals][slice][stride] int16 staging (allocated on first use)
+    cudaStream_t stream[kSlots] = {};
+    float* d_far[kSlots] = {};
+    float* d_mic[kSlots] = {};
+    float* d_err[kSlots] = {};
+    float* d_echo[kSlots] = {};
+    float* d_erle[kSlots] = {};
+    long long* d_n[kSlots] = {};
+    int16_t* d_pcm[kSlots] = {};   // [2 signals][slice][stride] int16 staging (allocated on first use)
     // page-locked staging for the small per-utterance arrays: a copy to / from pageable host memory
-    // would serialise the two-stream pipeline
-    float* h_erle[2] = {nullptr, nullptr};
-    long long* h_n[2] = {nullptr, nullptr};
-    int64_t pending_off[2] = {-1, -1};        // slice whose ERLE still sits in h_erle[k]
-    int64_t pending_nb[2] = {0, 0};
+    // would serialise the multi-stream pipeline
+    float* h_erle[kSlots] = {};
+    long long* h_n[kSlots] = {};
+    int64_t pending_off[kSlots] = {-1, -1, -1, -1};        // slice whose ERLE still sits in h_erle[k]
+    int64_t pending_nb[kSlots] = {};
 };
 
 // drain slot k: wait for its stream, hand the staged ERLE values to the caller
@@ -393,7 +398,7 @@ static int host_ctx_drain(aec_host_ctx* ctx, int k, float* erle_db) {
 
 extern "C" int aec_host_ctx_destroy(aec_host_ctx* ctx) {
     if (!ctx) return AEC_OK;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         if (ctx->stream[i]) cudaStreamSynchronize(ctx->stream[i]);
         cudaFree(ctx->d_far[i]);
         cudaFree(ctx->d_mic[i]);
@@ -419,7 +424,7 @@ extern "C" int aec_host_ctx_create(aec_host_ctx** out, int64_t slice_utterances,
     ctx->stride = (max_samples + 3) / 4 * 4;
     cudaError_t e = cudaGetDevice(&ctx->device);
     const size_t sig = (size_t)ctx->slice * (size_t)ctx->stride * sizeof(float);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    for (int i = 0; i < kSlots && e == cudaSuccess; ++i) {
         e = cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_far[i], sig);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_mic[i], sig);
@@ -452,10 +457,10 @@ extern "C" int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const fl
     const size_t dpitch = (size_t)ctx->stride * sizeof(float);
     int first_rc = AEC_OK;
     for (int64_t off = 0, it = 0; off < B; off += ctx->slice, ++it) {
-        const int k = (int)(it & 1);
+        const int k = (int)(it % kSlots);
         const int64_t nb = (B - off < ctx->slice) ? (B - off) : ctx->slice;
         cudaStream_t s = ctx->stream[k];
-        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (two slices ago) is done
+        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (kSlots slices ago) is done
         if (rc != AEC_OK) return rc;
         // contiguous rows on both sides -> one linear copy per signal (the DMA engines run linear copies
         // at full PCIe rate; pitched copies are only used for strided host layouts)
@@ -502,7 +507,7 @@ extern "C" int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const fl
             ctx->pending_nb[k] = nb;
         }
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         rc = host_ctx_drain(ctx, i, erle_db);
         if (rc != AEC_OK) return rc;
     }
@@ -519,7 +524,7 @@ extern "C" int aec_stage1_run_host_pcm16(aec_host_ctx* ctx, const int16_t* far, 
     if (B == 0) return AEC_OK;
     if (!far || !mic || !err) return AEC_EINVAL;
     const size_t pcm_sig = (size_t)ctx->slice * (size_t)ctx->stride;      // int16 elements per signal per slot
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kSlots; ++i)
         if (!ctx->d_pcm[i]) AEC_CUDA_CHECK(cudaMalloc(&ctx->d_pcm[i], 2 * pcm_sig * sizeof(int16_t)));
     const size_t row = (size_t)L * sizeof(float);
     const size_t dpitch = (size_t)ctx->stride * sizeof(float);
@@ -527,10 +532,10 @@ extern "C" int aec_stage1_run_host_pcm16(aec_host_ctx* ctx, const int16_t* far, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     int first_rc = AEC_OK;
     for (int64_t off = 0, it = 0; off < B; off += ctx->slice, ++it) {
-        const int k = (int)(it & 1);
+        const int k = (int)(it % kSlots);
         const int64_t nb = (B - off < ctx->slice) ? (B - off) : ctx->slice;
         cudaStream_t s = ctx->stream[k];
-        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (two slices ago) is done
+        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (kSlots slices ago) is done
         if (rc != AEC_OK) return rc;
         int16_t* pf = ctx->d_pcm[k];
         int16_t* pm = ctx->d_pcm[k] + pcm_sig;
@@ -579,7 +584,7 @@ extern "C" int aec_stage1_run_host_pcm16(aec_host_ctx* ctx, const int16_t* far, 
             ctx->pending_nb[k] = nb;
         }
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         rc = host_ctx_drain(ctx, i, erle_db);
         if (rc != AEC_OK) return rc;
     }

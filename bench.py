@@ -345,7 +345,7 @@ def main():
                "h2d_bytes_per_step": 2 * B * L * 4, "d2h_bytes_per_step": B * L * 4 + B * 4,
                "ms_per_step": float(dt[0]) * 1e3, "steps": k_e2e,
                "api": "aec_stage1_run_host (HostPipeline.run), float32 pinned host memory, 64-utterance slices, "
-                      "2 streams; PCIe-bound (H2D 1.31 GB/step)"}
+                      "4 slices in flight; PCIe-bound (H2D %.2f GB/step at ~50 GB/s with D2H running)" % (2 * B * L * 4 / 1e9)}
         e2e_match = bool(np.array_equal(he, err.cpu().numpy()))
         # wav-ingest variant: 16-bit PCM host buffers (what the wav files hold), converted on the GPU
         h16f = A.pinned_empty((B, L), dtype=np.int16)

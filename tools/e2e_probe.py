@@ -27,3 +27,10 @@ for sl in (32, 64, 128, 256, 512):
     dt = t(lambda: pipe.run(hf, hm, cfg, err=he), 4)
     print(f"slice {sl}: {dt*1e3:.2f} ms/step  {B*10/dt/1e3:.1f}k audio-s/s  ({3*gb/dt:.1f} GB/s total)")
     pipe.close()
+h16f, h16m = A.pinned_empty((B, L), dtype=np.int16), A.pinned_empty((B, L), dtype=np.int16)
+h16f[:] = np.clip(np.rint(hf * 32768.0), -32768, 32767).astype(np.int16); h16m[:] = np.clip(np.rint(hm * 32768.0), -32768, 32767).astype(np.int16)
+for sl in (16, 32, 64, 128):
+    pipe = A.HostPipeline(sl, L)
+    dt = t(lambda: pipe.run(h16f, h16m, cfg, err=he), 4)
+    print(f"pcm16 slice {sl}: {dt*1e3:.2f} ms/step  {B*10/dt/1e3:.1f}k audio-s/s")
+    pipe.close()
