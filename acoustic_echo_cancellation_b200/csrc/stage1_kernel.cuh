@@ -262,7 +262,9 @@ struct Stage1Smem {
     // window tables: analysis half-table [128] float2 + synthesis table [256] float2
     static constexpr size_t win_bytes = size_t(128 + 256) * sizeof(float2);
     // state of the self-mirrored bin 128 (one thread's worth; kept out of everybody's registers)
-    static constexpr size_t mid_bytes = (size_t(P) * (8 + 8 + 4) + 4 + 15) / 16 * 16;   // W, X, C per tap (+ Psi)
+    // state of bin 128: W, X, C per tap (+ Psi); ring kernels add the look-ahead buffers of that bin:
+    // X[128], Y[128] of the next chunk's frames (float4 each) and its packed E / Yhat entries (2 float2 each)
+    static constexpr size_t mid_bytes = (size_t(P) * (8 + 8 + 4) + 4 + 15) / 16 * 16 + (kRing ? size_t(F) * 32 : 0);
     static constexpr size_t ring_bytes = kRing ? size_t(P) * kRingPitch * sizeof(float2) : 0;
     // overlap-add: in-chunk tails live in the (dead after the inverse FFT) Zbuf tile of the frame
     // that produced them; only the last warp's tail crosses a chunk boundary -> one carry slot.
@@ -442,20 +444,33 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     const int k_own = side ? ((256 - (tid >> 1)) & 255) : (tid >> 1);
     const int k_oth = side ? (tid >> 1) : ((256 - (tid >> 1)) & 255);
     const int k_bin = side ? 256 - (tid >> 1) : (tid >> 1);      // true bin index 0..256 (ring column)
-    // Bin 128 is its own mirror, the 257th bin on 256 bin slots.  The last warp runs it TAP-PARALLEL
-    // (lane p owns tap p; the sums over taps are warp reductions), with the per-tap state in shared
-    // memory: no thread carries a second bin's state in registers and the extra work is ~1/5 of a
-    // regular bin pass instead of a serial P-tap loop on one lane.
-    // (For short filters the shuffle reductions cost more than they save -- measured 3-5 % on the
-    // whole kernel -- so short filters and NLMS keep the serial form: the last thread loads / steps / stores the
-    // bin's state in shared memory.)
+    // Bin 128 is its own mirror, the 257th bin on 256 bin slots.
+    //  * short filters (two-warp kernel): serial on one lane inside the frame loop, state in shared memory.
+    //  * 8 partitions and more: a serial pass on one lane would double the filter phase of its warp (every
+    //    other warp then waits at the barrier: measured 25 % of the frame time of the 16-partition Kalman
+    //    kernel).  The last warp runs it TAP-PARALLEL instead (lane p owns tap p, the sums over taps are
+    //    shuffle reductions) in a loop over the chunk's frames AFTER its regular bins -- no pair slot touches
+    //    entry 128 of the tiles -- with the tap state in registers for the duration of that loop only
+    //    (loaded from / stored to shared memory once per chunk).
     static_assert(P <= 32, "one lane per tap");
-    constexpr bool kMidTapParallel = (P >= 16 && ALGO == kAlgoKalman);   // measured: NLMS is faster serial
+    // (measured, ms per 2048 x 10 s: 16-partition Kalman 9.57 -> 9.02 against the former in-loop shared-memory
+    //  form; 16-partition NLMS on 8 warps 7.19 -> 5.96; 8 partitions are faster serial -- 2.12 vs 2.34 ms per
+    //  1024 -- as is the 4-warp 16-partition NLMS kernel, whose chunk is only 8 frames of a cheap serial pass)
+    constexpr bool kMidTapParallel = (P >= 16) && (ALGO == kAlgoKalman || NW == 8);
+    // Ring kernels (8 warps, 8 frames per chunk): only warps 0-3 have synthesis work, warps 4-7 used to wait at
+    // the barrier.  They now run bin 128 of the NEXT chunk in that window.  X[128] and Y[128] need no FFT:
+    // e^{-2 pi i 128 n / 512} = (-i)^n, so they are four interleaved sums of the windowed samples, which the
+    // bulk copies for the next chunk have already delivered.  The serial recurrence of that bin -- 25 % of the
+    // frame time when it ran inside the filter phase -- is off the critical path altogether.
+    constexpr bool kMidAhead = kRing;
+    static_assert(!kMidAhead || (kMidTapParallel && F == 8 && NW == 8), "look-ahead needs the idle synthesis warps");
     static_assert(BinState<P, ALGO>::kFloats * sizeof(float) <= SM::mid_bytes, "mid-bin state does not fit");
     float2* midW = reinterpret_cast<float2*>(mid_state);           // [P]
     float2* midX = midW + P;                                       // [P]
     float* midC = reinterpret_cast<float*>(midX + P);              // [P]
     float* midPsi = midC + P;                                      // [1]
+    float4* midXY = reinterpret_cast<float4*>(mid_state + (size_t(P) * 20 + 4 + 15) / 16 * 4);   // [F] X128.re,.im, Y128.re,.im
+    float2* midE = reinterpret_cast<float2*>(midXY + F);           // [F][2] packed tile entries 128 of E and Yhat
     if constexpr (kMidTapParallel) {
         if (warp == NW - 1 && lane < P) {
             midW[lane] = make_float2(0.f, 0.f);
@@ -469,6 +484,145 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         st_mid.store(mid_state);
     }
     const float2 w_mid = make_float2(0.f, -1.f);
+
+    // ---- bin 128 of the chunk starting at frame tc0, run by warps F/2 .. NW-1 (ring kernels) --------
+    // step 1 (all four warps, two frames each): X[128], Y[128] straight from the staged samples;
+    // step 2 (last warp, one lane per tap): the recurrence over the chunk's frames, tap state in registers.
+    auto mid_ahead = [&](int tc0, uint32_t parity) {
+      if constexpr (kMidAhead) {
+        mbar_wait(mbar, parity);                                   // the chunk's hops have landed
+        {
+            // step 1: this warp's two frames x two signals as four independent sums (one joint reduction)
+            const int tl0 = (warp - F / 2) * 2;
+            float r[4], q[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                int t = tc0 + tl0 + j;
+                t = t < T ? t : T - 1;                             // (past the end: recomputes a valid frame, not stored)
+#pragma unroll
+                for (int sig = 0; sig < 2; ++sig) {
+                    const float* s0 = stage + (sig * R + (t % R)) * 256 + 2 * lane;
+                    const float* s1 = stage + (sig * R + ((t + 1) % R)) * 256 + 2 * lane;
+                    float a = 0.f, b2 = 0.f;                       // sums over n = 0 (2) mod 4 and n = 1 (3) mod 4
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 w = win_a[lane + 32 * i];     // 0.5 hann[2m], 0.5 hann[2m+1], m = lane + 32 i
+                        const float2 x0 = *reinterpret_cast<const float2*>(s0 + 64 * i);
+                        const float2 x1 = *reinterpret_cast<const float2*>(s1 + 64 * i);
+                        a = fmaf(x0.x, w.x, a);
+                        b2 = fmaf(x0.y, w.y, b2);
+                        a = fmaf(x1.x, 0.5f - w.x, a);             // hann[n + 256] = 1 - hann[n]
+                        b2 = fmaf(x1.y, 0.5f - w.y, b2);
+                    }
+                    // (-i)^n: even lanes hold n = 0, 1 (mod 4): +a, -i b ; odd lanes n = 2, 3: -a, +i b
+                    r[2 * j + sig] = (lane & 1) ? -a : a;
+                    q[2 * j + sig] = (lane & 1) ? b2 : -b2;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    r[v] += __shfl_xor_sync(0xffffffffu, r[v], o);
+                    q[v] += __shfl_xor_sync(0xffffffffu, q[v], o);
+                }
+            }
+            if (lane < 2 && tc0 + tl0 + lane < T)                  // (the table carries the 1/2)
+                midXY[tl0 + lane] = lane == 0 ? make_float4(2.f * r[0], 2.f * q[0], 2.f * r[1], 2.f * q[1])
+                                              : make_float4(2.f * r[2], 2.f * q[2], 2.f * r[3], 2.f * q[3]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"((NW - F / 2) * 32) : "memory");     // warps F/2 .. NW-1 only
+        if (warp == NW - 1) {
+            // step 2: the recurrence, TPL taps per lane on P/TPL lanes (log2 of that many shuffle steps per sum),
+            // tap state in registers for the chunk; everything that does not depend on the error of the
+            // current frame (next history, powers) is kept off the frame-to-frame dependency chain
+            // (taps per lane measured on the 16-partition Kalman filter, 4096 x 10 s: 1 -> 17.6 ms, 2 -> 18.0, 4 -> 18.2)
+            constexpr int TPL = 1;                        // taps per lane
+            constexpr int kLanes = P / TPL;               // lanes carrying taps (power of two)
+            static_assert(P % TPL == 0 && (kLanes & (kLanes - 1)) == 0 && kLanes <= 32, "taps per lane");
+            auto wsum4 = [](float v) {
+#pragma unroll
+                for (int o = 1; o < kLanes; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                return v;
+            };
+            const bool tap = lane < kLanes;   // the other lanes carry zeros
+            const int p0 = (lane & (kLanes - 1)) * TPL;
+            float2 w[TPL], xp[TPL];
+            float cv[TPL];
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                w[i] = tap ? midW[p0 + i] : make_float2(0.f, 0.f);
+                xp[i] = tap ? midX[p0 + i] : make_float2(0.f, 0.f);      // tap's spectrum one frame ago
+                cv[i] = (ALGO == kAlgoKalman && tap) ? midC[p0 + i] : 0.f;
+            }
+            float psi = (ALGO == kAlgoKalman) ? *midPsi : 0.f;
+#pragma unroll 1
+            for (int tl = 0; tl < F; ++tl) {
+                if (tc0 + tl < T) {
+                    const float4 xy = midXY[tl];
+                    const float2 yn = make_float2(xy.z, xy.w);
+                    // tap p sees the spectrum tap p-1 saw one frame ago
+                    float2 x[TPL];
+                    x[0] = make_float2(__shfl_up_sync(0xffffffffu, xp[TPL - 1].x, 1), __shfl_up_sync(0xffffffffu, xp[TPL - 1].y, 1));
+                    if (lane == 0) x[0] = make_float2(xy.x, xy.y);
+                    if (!tap) x[0] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 1; i < TPL; ++i) x[i] = xp[i - 1];
+                    float2 ya = make_float2(0.f, 0.f);
+                    float x2[TPL], pw = 0.f;
+#pragma unroll
+                    for (int i = 0; i < TPL; ++i) {
+                        ya = cfma(w[i], x[i], ya);
+                        x2[i] = fmaf(x[i].x, x[i].x, x[i].y * x[i].y);
+                        pw = (ALGO == kAlgoKalman) ? fmaf(cv[i], x2[i], pw) : pw + x2[i];
+                    }
+                    const float2 yh = make_float2(wsum4(ya.x), wsum4(ya.y));
+                    pw = wsum4(pw);
+                    const float2 e = csub(yn, yh);
+                    if constexpr (ALGO == kAlgoNlms) {
+                        const float g = prm.mu * rcp_fast(pw + prm.delta);
+                        const float2 ge = make_float2(g * e.x, g * e.y);
+#pragma unroll
+                        for (int i = 0; i < TPL; ++i) w[i] = cfmac(x[i], ge, w[i]);
+                    } else {
+                        psi = fmaf(prm.klam, psi, prm.koml * fmaf(e.x, e.x, e.y * e.y));
+                        const float rd = __frcp_rn(pw + psi + prm.keps);
+#pragma unroll
+                        for (int i = 0; i < TPL; ++i) {
+                            const float gs = cv[i] * rd;
+                            float2 wn = cfma(make_float2(gs * x[i].x, -gs * x[i].y), e, w[i]);
+                            wn = make_float2(prm.ka * wn.x, prm.ka * wn.y);
+                            w[i] = wn;
+                            cv[i] = fmaf(prm.ka2 * (1.f - gs * x2[i]), cv[i], prm.kq * fmaf(wn.x, wn.x, wn.y * wn.y));
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < TPL; ++i) xp[i] = x[i];
+                    if (lane == 0) {
+                        float2 gk, gm;
+                        pack_pair(e, e, w_mid, gk, gm);
+                        midE[2 * tl] = gk;
+                        pack_pair(yh, yh, w_mid, gk, gm);
+                        midE[2 * tl + 1] = gk;
+                    }
+                }
+            }
+            if (tap) {
+#pragma unroll
+                for (int i = 0; i < TPL; ++i) {
+                    midW[p0 + i] = w[i];
+                    midX[p0 + i] = xp[i];
+                    if constexpr (ALGO == kAlgoKalman) midC[p0 + i] = cv[i];
+                }
+            }
+            if constexpr (ALGO == kAlgoKalman) if (lane == 0) *midPsi = psi;
+        }
+      }
+    };
+    if constexpr (kMidAhead) {
+        __syncthreads();                      // window table, tap state and the producer's manual-path stores
+        if (warp >= F / 2) mid_ahead(0, 0u);
+    }
 
     float acc_e = 0.f;     // ERLE energies in ONE register: lanes 16-31 accumulate the microphone, lanes 0-15 the error
 
@@ -515,6 +669,13 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         AEC_TICK(4);                         // produce
 
         // ================= phase B : per-bin recurrence =================
+        if constexpr (kMidAhead) {
+            // entries 128 of the tiles (no pair slot touches them): E / Yhat of bin 128, computed one chunk ahead
+            if (tid < F && t0 + tid < T) {
+                zbuf[(tid * 2 + 0) * kTilePitch + 128] = midE[2 * tid];
+                if constexpr (ECHO) zbuf[(tid * 2 + 1) * kTilePitch + 128] = midE[2 * tid + 1];
+            }
+        }
         // (frame loop deliberately NOT unrolled: the whole chunk loop must fit the 32 KB
         //  instruction cache; the price is the register moves of the history shift)
 #pragma unroll 1
@@ -590,56 +751,67 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                         }
                     }
                 }
-                if constexpr (kMidTapParallel) if (warp == NW - 1) {  // self-mirrored bin 128, one lane per tap
-                    // butterfly over the (power-of-two padded) tap lanes only: log2(P) steps
-                    constexpr int kTapLanes = P <= 1 ? 1 : P <= 2 ? 2 : P <= 4 ? 4 : P <= 8 ? 8 : P <= 16 ? 16 : 32;
-                    auto wsum = [](float v) {
+            }
+        }
+        if constexpr (kMidTapParallel && !kMidAhead) {
+            if (warp == NW - 1) {             // self-mirrored bin 128, one lane per tap, whole chunk
+                // butterfly over the (power-of-two padded) tap lanes only: log2(P) steps
+                constexpr int kTapLanes = P <= 8 ? 8 : P <= 16 ? 16 : 32;
+                auto wsum = [](float v) {
 #pragma unroll
-                        for (int o = kTapLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                        return v;
-                    };
-                    float2 xn, yn, unused;
-                    unpack_pair(zf[128], zf[128], w_mid, xn, unused);
-                    unpack_pair(zm[128], zm[128], w_mid, yn, unused);
-                    // tap p sees the spectrum tap p-1 saw one frame ago
-                    const bool tap = lane < P;               // lanes beyond the filter length carry zeros
-                    float2 x = (lane == 0) ? xn : (tap ? midX[lane - 1] : make_float2(0.f, 0.f));
-                    float2 w = tap ? midW[lane] : make_float2(0.f, 0.f);
-                    const float2 prod = cmul(w, x);
-                    const float2 yh = make_float2(wsum(prod.x), wsum(prod.y));
-                    const float2 e = csub(yn, yh);
-                    const float x2 = fmaf(x.x, x.x, x.y * x.y);
-                    if constexpr (ALGO == kAlgoNlms) {
-                        const float g = prm.mu * rcp_fast(wsum(x2) + prm.delta);
-                        w = cfmac(x, make_float2(g * e.x, g * e.y), w);
-                    } else {
-                        float c = tap ? midC[lane] : 0.f;
-                        const float psi = fmaf(prm.klam, *midPsi, prm.koml * fmaf(e.x, e.x, e.y * e.y));
-                        const float rd = __frcp_rn(wsum(c * x2) + psi + prm.keps);
-                        const float gs = c * rd;
-                        w = cfma(make_float2(gs * x.x, -gs * x.y), e, w);
-                        w = make_float2(prm.ka * w.x, prm.ka * w.y);
-                        c = fmaf(prm.ka2 * (1.f - gs * x2), c, prm.kq * fmaf(w.x, w.x, w.y * w.y));
-                        __syncwarp();
-                        if (tap) midC[lane] = c;
-                        if (lane == 0) *midPsi = psi;
-                    }
-                    __syncwarp();            // every lane has read its neighbour's X
-                    if (tap) {
-                        midX[lane] = x;
-                        midW[lane] = w;
-                    }
-                    if (lane == 0) {
-                        float2 gk, gm;
-                        pack_pair(e, e, w_mid, gk, gm);
-                        zf[128] = gk;
-                        if constexpr (ECHO) {
-                            pack_pair(yh, yh, w_mid, gk, gm);
-                            zm[128] = gk;
+                    for (int o = kTapLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    return v;
+                };
+                const bool tap = lane < P;    // lanes beyond the filter length carry zeros
+                float2 w = tap ? midW[lane] : make_float2(0.f, 0.f);
+                float2 xp = tap ? midX[lane] : make_float2(0.f, 0.f);     // this tap's spectrum one frame ago
+                float cv = (ALGO == kAlgoKalman && tap) ? midC[lane] : 0.f;
+                float psi = (ALGO == kAlgoKalman) ? *midPsi : 0.f;
+#pragma unroll 1
+                for (int tl = 0; tl < F; ++tl) {
+                    if (t0 + tl < T) {
+                        float2* zf = zbuf + (tl * 2 + 0) * kTilePitch;
+                        float2* zm = zbuf + (tl * 2 + 1) * kTilePitch;
+                        float2 xn, yn, unused;
+                        unpack_pair(zf[128], zf[128], w_mid, xn, unused);
+                        unpack_pair(zm[128], zm[128], w_mid, yn, unused);
+                        // tap p sees the spectrum tap p-1 saw one frame ago
+                        float2 x = make_float2(__shfl_up_sync(0xffffffffu, xp.x, 1), __shfl_up_sync(0xffffffffu, xp.y, 1));
+                        if (lane == 0) x = xn;
+                        if (!tap) x = make_float2(0.f, 0.f);
+                        const float2 prod = cmul(w, x);
+                        const float2 yh = make_float2(wsum(prod.x), wsum(prod.y));
+                        const float2 e = csub(yn, yh);
+                        const float x2 = fmaf(x.x, x.x, x.y * x.y);
+                        if constexpr (ALGO == kAlgoNlms) {
+                            const float g = prm.mu * rcp_fast(wsum(x2) + prm.delta);
+                            w = cfmac(x, make_float2(g * e.x, g * e.y), w);
+                        } else {
+                            psi = fmaf(prm.klam, psi, prm.koml * fmaf(e.x, e.x, e.y * e.y));
+                            const float rd = __frcp_rn(wsum(cv * x2) + psi + prm.keps);
+                            const float gs = cv * rd;
+                            w = cfma(make_float2(gs * x.x, -gs * x.y), e, w);
+                            w = make_float2(prm.ka * w.x, prm.ka * w.y);
+                            cv = fmaf(prm.ka2 * (1.f - gs * x2), cv, prm.kq * fmaf(w.x, w.x, w.y * w.y));
+                        }
+                        xp = x;
+                        if (lane == 0) {
+                            float2 gk, gm;
+                            pack_pair(e, e, w_mid, gk, gm);
+                            zf[128] = gk;
+                            if constexpr (ECHO) {
+                                pack_pair(yh, yh, w_mid, gk, gm);
+                                zm[128] = gk;
+                            }
                         }
                     }
-                    __syncwarp();
                 }
+                if (tap) {
+                    midW[lane] = w;
+                    midX[lane] = xp;
+                    if constexpr (ALGO == kAlgoKalman) midC[lane] = cv;
+                }
+                if constexpr (ALGO == kAlgoKalman) if (lane == 0) *midPsi = psi;
             }
         }
         AEC_TICK(5);                         // phase B
@@ -698,6 +870,10 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                 // (16 registers live across the whole chunk loop -> spills)
                 head[sgn][r] = u[r];
             }
+        }
+        if constexpr (kMidAhead) {
+            // the warps without synthesis work run bin 128 of the next chunk (see mid_ahead)
+            if (!synth_warp && t0 + F < T) mid_ahead(t0 + F, static_cast<uint32_t>((c + 1) & 1));
         }
         AEC_TICK(7);                         // phase C (inverse FFT + in-warp overlap)
         __syncthreads();
