@@ -94,7 +94,8 @@ int aec_stage1_run(const float* far, const float* mic, float* err, float* echo_e
 /* Host-buffer variant: the call a data-prep script makes with arrays that came out of
  * `librosa.load` (Stage2_lhm/generate_h5files/train_wav2h5.py:20-23) and whose results go to
  * `create_dataset` (train_wav2h5.py:39-42).  Copies are pipelined against the kernel in
- * slices of `ctx`'s capacity; pinned host memory (aec_host_alloc) gives full PCIe rate.
+ * slices of `ctx`'s capacity, four slices in flight (one stream each: H2D -> kernel -> D2H);
+ * pinned host memory (aec_host_alloc) gives full PCIe rate.
  * n_samples is a HOST int64 [B] or NULL. */
 typedef struct aec_host_ctx aec_host_ctx;
 int aec_host_ctx_create(aec_host_ctx** ctx, int64_t slice_utterances, int64_t max_samples);
