@@ -95,6 +95,33 @@ def test_ragged_and_degenerate_lengths(L):
     _run_case(4, 0, L, B=7, ragged=True)
 
 
+@pytest.mark.parametrize("P,algo,variant", [(16, 1, 0), (16, 0, 0), (16, 0, 8128), (8, 1, 0), (8, 0, 0)])
+@pytest.mark.parametrize("L", [16000 + 123, 8 * 256, 8 * 256 + 1, 9 * 256 - 1, 300])
+def test_long_filters_ragged_and_chunk_boundaries(P, algo, variant, L):
+    """The long-filter kernels (8 / 16 frames per chunk; for 16 partitions bin 128 runs one chunk ahead on the
+    warps without synthesis work): lengths around the chunk boundary, ragged batches with 0- and 1-hop
+    utterances, echo output on."""
+    _run_case(P, algo, L, B=7, ragged=True, variant=variant)
+
+
+def test_long_filter_unaligned_rows():
+    """16-partition Kalman on rows that are not 16-byte aligned: every hop goes through the predicated-load
+    path, which the look-ahead job of bin 128 reads as well."""
+    L, B = 16001, 3
+    d = synth.make_batch(0, B, L, rir_len=4096)
+    ref = O.stage1(d["far"], d["mic"], O.AecConfig(partitions=16, algo=O.ALGO_KALMAN))
+    bf = torch.zeros(B, L + 3, device="cuda")
+    bm = torch.zeros(B, L + 3, device="cuda")
+    bo = torch.zeros(B, L + 3, device="cuda")
+    bf[:, 1:L + 1] = _cuda(d["far"])
+    bm[:, 1:L + 1] = _cuda(d["mic"])
+    cfg = A.Stage1Config(partitions=16, algo=A.ALGO_KALMAN)
+    err = A.stage1_aec(bf[:, 1:L + 1], bm[:, 1:L + 1], cfg, out=bo[:, 1:L + 1]).cpu().numpy()
+    n = ref["err"].shape[1]
+    assert np.abs(err[:, :n] - ref["err"]).max() <= TOL_ERR
+    assert float(bo[:, 0].abs().max()) == 0 and float(bo[:, L + 1:].abs().max()) == 0   # no stray writes
+
+
 @pytest.mark.parametrize("variant", [2128, 2168, 4128, 4096, 1255, 1200])
 def test_tuning_variants_agree(variant):
     _run_case(4, 0, 16000 + 256, variant=variant, echo=False)   # tuning variants are built without the echo output
