@@ -234,15 +234,19 @@ __global__ void __launch_bounds__(256) __maxnreg__(REGS) stage1_n1024_kernel(con
 #pragma unroll
             for (int sgn = 0; sgn < NSIG; ++sgn) {
                 const float2* tail_src = (warp == 0) ? carry + sgn * 256 : zbuf + ((tl - 1) * 2 + sgn) * FP;
+                // conditions decided once, predicated straight-line loop body (see stage1_kernel.cuh)
+                const bool vec = prm.vec_out != 0;
+                float* dst = out_b[sgn] + (long long)(t - 1) * HOP + 2 * h + 32 * hb;
+                float en = 0.f;
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const float2 tl2 = tail_src[h + 16 * hb + 32 * s];
                     const float2 o = make_float2(head[sgn][s].x + tl2.x, head[sgn][s].y + tl2.y);
-                    float* dst = out_b[sgn] + (long long)(t - 1) * HOP + 2 * h + 32 * hb + 64 * s;
-                    if (prm.vec_out) st_stream_f2(dst, o);
-                    else { st_stream_f1(dst, o.x); st_stream_f1(dst + 1, o.y); }
-                    if (sgn == 0 && t - 1 >= prm.erle_skip_hops) acc_err = fmaf(o.x, o.x, fmaf(o.y, o.y, acc_err));
+                    if (vec) st_stream_f2(dst + 64 * s, o);
+                    else { st_stream_f1(dst + 64 * s, o.x); st_stream_f1(dst + 64 * s + 1, o.y); }
+                    en = fmaf(o.x, o.x, fmaf(o.y, o.y, en));
                 }
+                if (sgn == 0 && t - 1 >= prm.erle_skip_hops) acc_err += en;
             }
         }
         // the last frame's tail crosses into the next chunk (warp 0 has consumed the old carry)
