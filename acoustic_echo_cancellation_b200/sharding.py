@@ -28,24 +28,37 @@ def shard_sizes(n_items: int, world: int) -> List[int]:
     return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
 
 
-def gather_metrics(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+def gather_metrics(local: torch.Tensor, n_items: int, group=None, async_op: bool = False):
     """All-gather per-utterance metrics of the contiguous shards back into utterance order.
-    ``local`` is this rank's 1-D slice (length ``shard_range(n_items, rank, world)``)."""
+    ``local`` is this rank's 1-D slice (length ``shard_range(n_items, rank, world)``).
+
+    ``async_op=True`` returns ``(tensor, work)``: the collective runs on the backend's own stream and the
+    caller's stream is not made to wait until ``work.wait()`` -- the next batch's kernel can start while the
+    metrics of this one are still in flight (``tensor`` is valid after ``work.wait()``; ``work`` is None when
+    there is nothing to wait for)."""
     if not dist.is_available() or not dist.is_initialized():
         if local.numel() != n_items:
             raise ValueError("single process must hold every item")
-        return local
+        return (local, None) if async_op else local
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     sizes = shard_sizes(n_items, world)
     if local.numel() != sizes[rank]:
         raise ValueError(f"rank {rank} holds {local.numel()} items, expected {sizes[rank]}")
     width = max(sizes) if sizes else 0
+    if min(sizes) == width and dist.get_backend(group) == "nccl":
+        # equal shards (the usual case): one collective straight into the result, no staging copies
+        out = torch.empty(world * width, dtype=local.dtype, device=local.device)
+        work = dist.all_gather_into_tensor(out, local.contiguous(), group=group, async_op=async_op)
+        return (out, work) if async_op else out
     padded = torch.zeros(width, dtype=local.dtype, device=local.device)
     padded[: local.numel()] = local
     parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)
-    return torch.cat([p[:s] for p, s in zip(parts, sizes)])
+    work = dist.all_gather(parts, padded, group=group, async_op=async_op)
+    if async_op:
+        work.wait()      # ragged shards are re-assembled on the caller's stream
+    out = torch.cat([p[:s] for p, s in zip(parts, sizes)])
+    return (out, None) if async_op else out
 
 
 def merge_filelists(local_paths: List[str], group=None) -> List[str]:

@@ -287,12 +287,16 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
     ev0.record()
+    pending = []
     for i in range(args.steps):
         kev[i][0].record()
         erle = A.stage1_aec(far, mic, cfg, out=err, return_erle=True)[1]
         kev[i][1].record()
-        if world > 1:
-            erle = sharding.gather_metrics(erle, n_total)
+        if world > 1:     # metrics gather of step i runs on NCCL's stream under the kernel of step i + 1
+            pending.append(sharding.gather_metrics(erle, n_total, async_op=True))
+    for erle, work in pending:
+        if work is not None:
+            work.wait()   # every step's gathered metrics are complete inside the timed region
     ev1.record()
     barrier()
     wall1 = time.perf_counter()

@@ -32,6 +32,14 @@ def _worker(rank, world, port, n_items, ret):
     lo, hi = sharding.shard_range(n_items, rank, world)
     local = torch.arange(lo, hi, dtype=torch.float32) * 0.5      # stands for per-utterance ERLE
     full = sharding.gather_metrics(local, n_items)
+    full_async, work = sharding.gather_metrics(local, n_items, async_op=True)    # overlapped form used by bench.py
+    if work is not None:
+        work.wait()
+    assert torch.equal(full, full_async)
+    even, work = sharding.gather_metrics(torch.full((3,), float(rank)), 3 * world, async_op=True)   # equal shards
+    if work is not None:
+        work.wait()
+    assert even.tolist() == [float(r) for r in range(world) for _ in range(3)]
     files = sharding.merge_filelists([f"tr_{i}.ex" for i in range(lo, hi)])
     ret[rank] = (full.tolist(), files)
     dist.destroy_process_group()
@@ -52,6 +60,8 @@ def test_gather_metrics_world_size_2_gloo():
 def test_gather_metrics_single_process_passthrough():
     x = torch.arange(5, dtype=torch.float32)
     assert torch.equal(sharding.gather_metrics(x, 5), x)
+    y, work = sharding.gather_metrics(x, 5, async_op=True)
+    assert work is None and torch.equal(y, x)
 
 
 def test_ragged_batching_pads_and_unpads():
