@@ -402,6 +402,14 @@ def main():
                 "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                         "peak_source": hbm_src}}
 
+    if args.config == 2:
+        # context for `frac` (static analysis of the measured SASS, profiles/r1_fp32_issue_rates.txt): FFMAs with three
+        # distinct register sources issue at 0.64 per cycle per scheduler on this part; with them counted at that rate the
+        # instruction stream of this kernel cannot exceed ~9.1 M audio-s/s per GPU (0.44 of the FFMA peak)
+        ceiling = 9.1e6
+        roofline["issue_limited_ceiling"] = {"audio_s_per_s_per_gpu": ceiling, "frac_of_ceiling": (value / world) / ceiling,
+                                             "source": "profiles/r1_fp32_issue_rates.txt, DESIGN.md section 5 (Roofline)"}
+
     # ---- CPU baseline: the C port on this box's cores, bounded sample of the same workload ----
     cpu = None
     if not args.no_cpu_baseline:
