@@ -438,12 +438,23 @@ int set_smem(K kern, size_t bytes) {
 
 using namespace aec;
 
+static constexpr int64_t kMaxGridY = 65535;
+
 extern "C" int aec_stft(const float* x, float* spec, int64_t B, int64_t L, int64_t in_stride, int32_t frame,
                         void* cuda_stream) {
     if (B < 0 || L < 0 || in_stride < L) return AEC_EINVAL;
     if (frame != 512 && frame != 1024) return AEC_EINVAL;
     if (B == 0) return AEC_OK;
-    if (!x || !spec || B > 65535) return AEC_EINVAL;
+    if (!x || !spec) return AEC_EINVAL;
+    if (B > kMaxGridY) {        // grid.y carries the utterance index: larger batches go in slices
+        const long long per = 2LL * (frame / 2 + 1) * aec_num_frames(L, frame);
+        for (int64_t off = 0; off < B; off += kMaxGridY) {
+            const int rc2 = aec_stft(x + off * in_stride, spec + off * per, (B - off < kMaxGridY) ? B - off : kMaxGridY, L,
+                                     in_stride, frame, cuda_stream);
+            if (rc2 != AEC_OK) return rc2;
+        }
+        return AEC_OK;
+    }
     Tables tab;
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
@@ -474,7 +485,16 @@ extern "C" int aec_istft(const float* spec, float* y, int64_t B, int64_t T, int6
     if (frame != 512 && frame != 1024) return AEC_EINVAL;
     if (T >= 1 && out_stride < (T - 1) * (frame / 2)) return AEC_EINVAL;
     if (B == 0 || T <= 1) return AEC_OK;
-    if (!spec || !y || B > 65535) return AEC_EINVAL;
+    if (!spec || !y) return AEC_EINVAL;
+    if (B > kMaxGridY) {
+        const long long per = 2LL * (frame / 2 + 1) * T;
+        for (int64_t off = 0; off < B; off += kMaxGridY) {
+            const int rc2 = aec_istft(spec + off * per, y + off * out_stride, (B - off < kMaxGridY) ? B - off : kMaxGridY, T,
+                                      out_stride, frame, cuda_stream);
+            if (rc2 != AEC_OK) return rc2;
+        }
+        return AEC_OK;
+    }
     Tables tab;
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
@@ -506,7 +526,17 @@ extern "C" int aec_features(const float* mic, const float* ref, const float* erb
     if (B < 0 || L < 0 || in_stride < L || bands < 1 || bands > 64) return AEC_EINVAL;
     if (frame != 512) return frame == 1024 ? AEC_EUNSUPPORTED : AEC_EINVAL;
     if (B == 0) return AEC_OK;
-    if (!mic || !ref || !erb || !feat || B > 65535) return AEC_EINVAL;
+    if (!mic || !ref || !erb || !feat) return AEC_EINVAL;
+    if (B > kMaxGridY) {
+        const long long per = 2LL * bands * aec_num_frames(L, frame);
+        for (int64_t off = 0; off < B; off += kMaxGridY) {
+            const int rc2 = aec_features(mic + off * in_stride, ref + off * in_stride, erb, feat + off * per,
+                                         (B - off < kMaxGridY) ? B - off : kMaxGridY, L, in_stride, frame, bands,
+                                         shift_mic, shift_ref, cuda_stream);
+            if (rc2 != AEC_OK) return rc2;
+        }
+        return AEC_OK;
+    }
     Tables tab;
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;

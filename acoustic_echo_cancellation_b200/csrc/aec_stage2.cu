@@ -286,7 +286,16 @@ extern "C" int aec_stage2_synth(const float* mic, const float* est_erb, const fl
     const long long T = aec_num_frames(L, frame);
     if (T >= 1 && out_stride < (T - 1) * 256) return AEC_EINVAL;
     if (B == 0 || T <= 1) return AEC_OK;
-    if (!mic || !est_erb || !erb || !out || B > 65535) return AEC_EINVAL;
+    if (!mic || !est_erb || !erb || !out) return AEC_EINVAL;
+    if (B > 65535) {            // grid.y carries the utterance index: larger batches go in slices
+        for (int64_t off = 0; off < B; off += 65535) {
+            const int rc2 = aec_stage2_synth(mic + off * in_stride, est_erb + off * T * kH, erb, out + off * out_stride,
+                                             (B - off < 65535) ? B - off : 65535, L, in_stride, out_stride, frame, bands,
+                                             shift_mic, cuda_stream);
+            if (rc2 != AEC_OK) return rc2;
+        }
+        return AEC_OK;
+    }
     Tables tab;
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;

@@ -289,6 +289,25 @@ def test_stage2_little_net_inference_matches_reference_module():
     assert np.abs(out - ref64).max() < 2e-4 * np.abs(ref64).max()
 
 
+def test_batches_larger_than_the_grid_y_limit():
+    """More than 65535 utterances per call (grid.y of the operator kernels carries the utterance index; the stage-1
+    kernel uses grid.x): results must equal the same rows processed in a small batch."""
+    B, L = 65535 + 700, 1024
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = 0.2 * torch.randn(B, L, device="cuda", generator=g)
+    stft, istft = A.ConvSTFT(512, 256, 512, "hann", "complex"), A.ConviSTFT(512, 256, 512, "hann", "complex")
+    s = stft(x)
+    y = istft(s)
+    rows = [0, 65534, 65535, B - 1]
+    xs = x[rows].contiguous()
+    assert torch.equal(s[rows], stft(xs)) and torch.equal(y[rows], istft(stft(xs)))
+    erb = torch.from_numpy(O.erb_filterbank()).float().cuda()
+    f = A.stage2_features(x, torch.roll(x, 5, dims=1), erb, in_norm=False)
+    assert torch.equal(f[rows], A.stage2_features(xs, torch.roll(x, 5, dims=1)[rows].contiguous(), erb, in_norm=False))
+    err = A.stage1_aec(torch.roll(x, 3, dims=1), x, A.Stage1Config(partitions=2))
+    assert torch.equal(err[rows], A.stage1_aec(torch.roll(x, 3, dims=1)[rows].contiguous(), xs, A.Stage1Config(partitions=2)))
+
+
 def test_stft_3d_input_and_ctor_errors():
     x = torch.randn(2, 1, 2048, device="cuda")
     s = A.ConvSTFT(512, 256, 512, "hann", "complex")(x)
