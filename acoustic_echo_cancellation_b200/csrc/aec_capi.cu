@@ -387,6 +387,15 @@ struct aec_host_ctx {
     int64_t pending_nb[kSlots] = {};
 };
 
+// Utterances of the next slice.  The upload engine is the bottleneck and stays busy to the end; what follows the last
+// upload (kernel: the 0.65 ms latency of one utterance, then its download) is pure tail, so the last slices are tapered
+// (.. 64, 32, 16, 16) to leave a small download behind the last kernel.
+static int64_t host_slice(int64_t slice, int64_t remaining) {
+    if (remaining > slice) return slice;          // (never more than the context's capacity)
+    if (remaining <= 16) return remaining;
+    return (remaining + 1) / 2;
+}
+
 // drain slot k: wait for its stream, hand the staged ERLE values to the caller
 static int host_ctx_drain(aec_host_ctx* ctx, int k, float* erle_db) {
     AEC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream[k]));
@@ -456,9 +465,10 @@ extern "C" int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const fl
     const size_t row = (size_t)L * sizeof(float);
     const size_t dpitch = (size_t)ctx->stride * sizeof(float);
     int first_rc = AEC_OK;
-    for (int64_t off = 0, it = 0; off < B; off += ctx->slice, ++it) {
+    int64_t nb = 0;
+    for (int64_t off = 0, it = 0; off < B; off += nb, ++it) {
         const int k = (int)(it % kSlots);
-        const int64_t nb = (B - off < ctx->slice) ? (B - off) : ctx->slice;
+        nb = host_slice(ctx->slice, B - off);
         cudaStream_t s = ctx->stream[k];
         rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (kSlots slices ago) is done
         if (rc != AEC_OK) return rc;
@@ -531,9 +541,10 @@ extern "C" int aec_stage1_run_host_pcm16(aec_host_ctx* ctx, const int16_t* far, 
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     int first_rc = AEC_OK;
-    for (int64_t off = 0, it = 0; off < B; off += ctx->slice, ++it) {
+    int64_t nb = 0;
+    for (int64_t off = 0, it = 0; off < B; off += nb, ++it) {
         const int k = (int)(it % kSlots);
-        const int64_t nb = (B - off < ctx->slice) ? (B - off) : ctx->slice;
+        nb = host_slice(ctx->slice, B - off);
         cudaStream_t s = ctx->stream[k];
         rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (kSlots slices ago) is done
         if (rc != AEC_OK) return rc;
