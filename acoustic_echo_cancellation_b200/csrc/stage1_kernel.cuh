@@ -262,9 +262,10 @@ struct Stage1Smem {
     // window tables: analysis half-table [128] float2 + synthesis table [256] float2
     static constexpr size_t win_bytes = size_t(128 + 256) * sizeof(float2);
     // state of the self-mirrored bin 128 (one thread's worth; kept out of everybody's registers)
-    // state of bin 128: W, X, C per tap (+ Psi); ring kernels add the look-ahead buffers of that bin:
-    // X[128], Y[128] of the next chunk's frames (float4 each) and its packed E / Yhat entries (2 float2 each)
-    static constexpr size_t mid_bytes = (size_t(P) * (8 + 8 + 4) + 4 + 15) / 16 * 16 + (kRing ? size_t(F) * 32 : 0);
+    // state of bin 128: W, X, C per tap (+ Psi).  Ring kernels keep X as a contiguous history H[P + F] (the P past
+    // frames followed by the F frames of the chunk being looked ahead: P*8 bytes of it are the X slot above) and add
+    // Y[128] of those frames (float2 each) and the resulting E / Yhat (2 float2 each)
+    static constexpr size_t mid_bytes = (size_t(P) * (8 + 8 + 4) + 4 + 15) / 16 * 16 + (kRing ? size_t(P + F) * 8 + size_t(F) * 24 : 0);
     static constexpr size_t ring_bytes = kRing ? size_t(P) * kRingPitch * sizeof(float2) : 0;
     // overlap-add: in-chunk tails live in the (dead after the inverse FFT) Zbuf tile of the frame
     // that produced them; only the last warp's tail crosses a chunk boundary -> one carry slot.
@@ -469,12 +470,15 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     float2* midX = midW + P;                                       // [P]
     float* midC = reinterpret_cast<float*>(midX + P);              // [P]
     float* midPsi = midC + P;                                      // [1]
-    float4* midXY = reinterpret_cast<float4*>(mid_state + (size_t(P) * 20 + 4 + 15) / 16 * 4);   // [F] X128.re,.im, Y128.re,.im
-    float2* midE = reinterpret_cast<float2*>(midXY + F);           // [F][2] packed tile entries 128 of E and Yhat
+    // look-ahead buffers (ring kernels); midH[i] = X[128] at frame tc0 - P + i while chunk tc0 is being looked ahead
+    float2* midH = reinterpret_cast<float2*>(mid_state + (size_t(P) * 20 + 4 + 15) / 16 * 4);   // [P + F]
+    float2* midY = midH + P + F;                                   // [F]    Y[128] of the chunk's frames
+    float2* midE = midY + F;                                       // [F][2] E[128], Yhat[128] (packed when injected)
     if constexpr (kMidTapParallel) {
         if (warp == NW - 1 && lane < P) {
             midW[lane] = make_float2(0.f, 0.f);
             midX[lane] = make_float2(0.f, 0.f);
+            if constexpr (kRing) midH[lane] = make_float2(0.f, 0.f);       // X[t < 0] = 0
             midC[lane] = prm.kc0;
             if (lane == 0) *midPsi = 0.f;
         }
@@ -527,99 +531,67 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     q[v] += __shfl_xor_sync(0xffffffffu, q[v], o);
                 }
             }
-            if (lane < 2 && tc0 + tl0 + lane < T)                  // (the table carries the 1/2)
-                midXY[tl0 + lane] = lane == 0 ? make_float4(2.f * r[0], 2.f * q[0], 2.f * r[1], 2.f * q[1])
-                                              : make_float4(2.f * r[2], 2.f * q[2], 2.f * r[3], 2.f * q[3]);
+            if (lane < 2 && tc0 + tl0 + lane < T) {                // (the table carries the 1/2)
+                midH[P + tl0 + lane] = lane == 0 ? make_float2(2.f * r[0], 2.f * q[0]) : make_float2(2.f * r[2], 2.f * q[2]);
+                midY[tl0 + lane] = lane == 0 ? make_float2(2.f * r[1], 2.f * q[1]) : make_float2(2.f * r[3], 2.f * q[3]);
+            }
         }
         asm volatile("bar.sync 1, %0;" ::"n"((NW - F / 2) * 32) : "memory");     // warps F/2 .. NW-1 only
         if (warp == NW - 1) {
-            // step 2: the recurrence, TPL taps per lane on P/TPL lanes (log2 of that many shuffle steps per sum),
-            // tap state in registers for the chunk; everything that does not depend on the error of the
-            // current frame (next history, powers) is kept off the frame-to-frame dependency chain
-            // (taps per lane measured on the 16-partition Kalman filter, 4096 x 10 s: 1 -> 17.6 ms, 2 -> 18.0, 4 -> 18.2)
-            constexpr int TPL = 1;                        // taps per lane
-            constexpr int kLanes = P / TPL;               // lanes carrying taps (power of two)
-            static_assert(P % TPL == 0 && (kLanes & (kLanes - 1)) == 0 && kLanes <= 32, "taps per lane");
-            auto wsum4 = [](float v) {
+            // step 2: the recurrence, one lane per tap, tap state in registers for the chunk.  Lane p reads its far-end
+            // value of frame tl straight from the history (H[P + tl - p]): nothing but the filter taps, the covariances
+            // and Psi is carried from frame to frame, and only the sums over taps cross lanes.
+            constexpr int kLanes = P;
+            static_assert((kLanes & (kLanes - 1)) == 0 && kLanes <= 32, "one lane per tap");
+            auto wsum = [](float v) {
 #pragma unroll
                 for (int o = 1; o < kLanes; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 return v;
             };
             const bool tap = lane < kLanes;   // the other lanes carry zeros
-            const int p0 = (lane & (kLanes - 1)) * TPL;
-            float2 w[TPL], xp[TPL];
-            float cv[TPL];
-#pragma unroll
-            for (int i = 0; i < TPL; ++i) {
-                w[i] = tap ? midW[p0 + i] : make_float2(0.f, 0.f);
-                xp[i] = tap ? midX[p0 + i] : make_float2(0.f, 0.f);      // tap's spectrum one frame ago
-                cv[i] = (ALGO == kAlgoKalman && tap) ? midC[p0 + i] : 0.f;
-            }
+            const int pl = tap ? lane : 0;
+            float2 w = tap ? midW[pl] : make_float2(0.f, 0.f);
+            float cv = (ALGO == kAlgoKalman && tap) ? midC[pl] : 0.f;
             float psi = (ALGO == kAlgoKalman) ? *midPsi : 0.f;
-            // fully unrolled (8 frames): the X[128], Y[128] loads get immediate addresses and are hoisted off the
-            // frame-to-frame dependency chain (measured on config 3: rolled 17.75 ms, rolled + prefetch 18.0, unrolled 17.45)
-            float4 xy_next = midXY[0];
+            const float2* hp = midH + (P - pl);
+            // fully unrolled (8 frames): loads get immediate addresses and sit off the frame-to-frame dependency chain
 #pragma unroll
             for (int tl = 0; tl < F; ++tl) {
-                const float4 xy = xy_next;
-                if (tl + 1 < F) xy_next = midXY[tl + 1];
                 if (tc0 + tl < T) {
-                    const float2 yn = make_float2(xy.z, xy.w);
-                    // tap p sees the spectrum tap p-1 saw one frame ago
-                    float2 x[TPL];
-                    x[0] = make_float2(__shfl_up_sync(0xffffffffu, xp[TPL - 1].x, 1), __shfl_up_sync(0xffffffffu, xp[TPL - 1].y, 1));
-                    if (lane == 0) x[0] = make_float2(xy.x, xy.y);
-                    if (!tap) x[0] = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int i = 1; i < TPL; ++i) x[i] = xp[i - 1];
-                    float2 ya = make_float2(0.f, 0.f);
-                    float x2[TPL], pw = 0.f;
-#pragma unroll
-                    for (int i = 0; i < TPL; ++i) {
-                        ya = cfma(w[i], x[i], ya);
-                        x2[i] = fmaf(x[i].x, x[i].x, x[i].y * x[i].y);
-                        pw = (ALGO == kAlgoKalman) ? fmaf(cv[i], x2[i], pw) : pw + x2[i];
-                    }
-                    const float2 yh = make_float2(wsum4(ya.x), wsum4(ya.y));
-                    pw = wsum4(pw);
+                    float2 x = hp[tl];
+                    if (!tap) x = make_float2(0.f, 0.f);
+                    const float2 yn = midY[tl];
+                    const float2 prod = cmul(w, x);
+                    const float x2 = fmaf(x.x, x.x, x.y * x.y);
+                    const float2 yh = make_float2(wsum(prod.x), wsum(prod.y));
                     const float2 e = csub(yn, yh);
                     if constexpr (ALGO == kAlgoNlms) {
-                        const float g = prm.mu * rcp_fast(pw + prm.delta);
-                        const float2 ge = make_float2(g * e.x, g * e.y);
-#pragma unroll
-                        for (int i = 0; i < TPL; ++i) w[i] = cfmac(x[i], ge, w[i]);
+                        const float g = prm.mu * rcp_fast(wsum(x2) + prm.delta);
+                        w = cfmac(x, make_float2(g * e.x, g * e.y), w);
                     } else {
+                        const float sx = wsum(cv * x2);
                         psi = fmaf(prm.klam, psi, prm.koml * fmaf(e.x, e.x, e.y * e.y));
-                        const float rd = __frcp_rn(pw + psi + prm.keps);
-#pragma unroll
-                        for (int i = 0; i < TPL; ++i) {
-                            const float gs = cv[i] * rd;
-                            float2 wn = cfma(make_float2(gs * x[i].x, -gs * x[i].y), e, w[i]);
-                            wn = make_float2(prm.ka * wn.x, prm.ka * wn.y);
-                            w[i] = wn;
-                            cv[i] = fmaf(prm.ka2 * (1.f - gs * x2[i]), cv[i], prm.kq * fmaf(wn.x, wn.x, wn.y * wn.y));
-                        }
+                        const float rd = __frcp_rn(sx + psi + prm.keps);
+                        const float gs = cv * rd;
+                        w = cfma(make_float2(gs * x.x, -gs * x.y), e, w);
+                        w = make_float2(prm.ka * w.x, prm.ka * w.y);
+                        cv = fmaf(prm.ka2 * (1.f - gs * x2), cv, prm.kq * fmaf(w.x, w.x, w.y * w.y));
                     }
-#pragma unroll
-                    for (int i = 0; i < TPL; ++i) xp[i] = x[i];
                     if (lane == 0) {
-                        float2 gk, gm;
-                        pack_pair(e, e, w_mid, gk, gm);
-                        midE[2 * tl] = gk;
-                        pack_pair(yh, yh, w_mid, gk, gm);
-                        midE[2 * tl + 1] = gk;
+                        midE[2 * tl] = e;
+                        midE[2 * tl + 1] = yh;
                     }
                 }
             }
             if (tap) {
-#pragma unroll
-                for (int i = 0; i < TPL; ++i) {
-                    midW[p0 + i] = w[i];
-                    midX[p0 + i] = xp[i];
-                    if constexpr (ALGO == kAlgoKalman) midC[p0 + i] = cv[i];
-                }
+                midW[pl] = w;
+                if constexpr (ALGO == kAlgoKalman) midC[pl] = cv;
             }
             if constexpr (ALGO == kAlgoKalman) if (lane == 0) *midPsi = psi;
+            // slide the history: the last P frames become the past of the next chunk
+            const float2 keep = tap ? midH[F + pl] : make_float2(0.f, 0.f);
+            __syncwarp();
+            if (tap) midH[pl] = keep;
         }
       }
     };
@@ -676,8 +648,14 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         if constexpr (kMidAhead) {
             // entries 128 of the tiles (no pair slot touches them): E / Yhat of bin 128, computed one chunk ahead
             if (tid < F && t0 + tid < T) {
-                zbuf[(tid * 2 + 0) * kTilePitch + 128] = midE[2 * tid];
-                if constexpr (ECHO) zbuf[(tid * 2 + 1) * kTilePitch + 128] = midE[2 * tid + 1];
+                float2 gk, gm;
+                const float2 e = midE[2 * tid], yh = midE[2 * tid + 1];
+                pack_pair(e, e, w_mid, gk, gm);
+                zbuf[(tid * 2 + 0) * kTilePitch + 128] = gk;
+                if constexpr (ECHO) {
+                    pack_pair(yh, yh, w_mid, gk, gm);
+                    zbuf[(tid * 2 + 1) * kTilePitch + 128] = gk;
+                }
             }
         }
         // (frame loop deliberately NOT unrolled: the chunk loop is ~30 KB of executed SASS against a 32 KB
