@@ -22,6 +22,7 @@
 // cp.async.bulk + mbarrier) one chunk ahead of the analysis phase; spectra never touch HBM.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "fft_warp.cuh"
@@ -554,35 +555,45 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
             float cv = (ALGO == kAlgoKalman && tap) ? midC[pl] : 0.f;
             float psi = (ALGO == kAlgoKalman) ? *midPsi : 0.f;
             const float2* hp = midH + (P - pl);
-            // fully unrolled (8 frames): loads get immediate addresses and sit off the frame-to-frame dependency chain
+            // fully unrolled (8 frames).  A chunk that lies completely inside the utterance (all but the last one) runs
+            // without per-frame conditions, so that every load is hoisted to the top and only arithmetic and shuffles
+            // remain on the frame-to-frame chain; the reciprocal is MUFU + one Newton step written out (what __frcp_rn
+            // does on its fast path, without its range-check branch: D >= eps is far from the denormals).
+            auto run = [&](auto guard_tag) {
+                constexpr bool kGuard = decltype(guard_tag)::value;
 #pragma unroll
-            for (int tl = 0; tl < F; ++tl) {
-                if (tc0 + tl < T) {
-                    float2 x = hp[tl];
-                    if (!tap) x = make_float2(0.f, 0.f);
-                    const float2 yn = midY[tl];
-                    const float2 prod = cmul(w, x);
-                    const float x2 = fmaf(x.x, x.x, x.y * x.y);
-                    const float2 yh = make_float2(wsum(prod.x), wsum(prod.y));
-                    const float2 e = csub(yn, yh);
-                    if constexpr (ALGO == kAlgoNlms) {
-                        const float g = prm.mu * rcp_fast(wsum(x2) + prm.delta);
-                        w = cfmac(x, make_float2(g * e.x, g * e.y), w);
-                    } else {
-                        const float sx = wsum(cv * x2);
-                        psi = fmaf(prm.klam, psi, prm.koml * fmaf(e.x, e.x, e.y * e.y));
-                        const float rd = __frcp_rn(sx + psi + prm.keps);
-                        const float gs = cv * rd;
-                        w = cfma(make_float2(gs * x.x, -gs * x.y), e, w);
-                        w = make_float2(prm.ka * w.x, prm.ka * w.y);
-                        cv = fmaf(prm.ka2 * (1.f - gs * x2), cv, prm.kq * fmaf(w.x, w.x, w.y * w.y));
-                    }
-                    if (lane == 0) {
-                        midE[2 * tl] = e;
-                        midE[2 * tl + 1] = yh;
+                for (int tl = 0; tl < F; ++tl) {
+                    if (!kGuard || tc0 + tl < T) {
+                        float2 x = hp[tl];
+                        if (!tap) x = make_float2(0.f, 0.f);
+                        const float2 yn = midY[tl];
+                        const float2 prod = cmul(w, x);
+                        const float x2 = fmaf(x.x, x.x, x.y * x.y);
+                        const float2 yh = make_float2(wsum(prod.x), wsum(prod.y));
+                        const float2 e = csub(yn, yh);
+                        if constexpr (ALGO == kAlgoNlms) {
+                            const float g = prm.mu * rcp_fast(wsum(x2) + prm.delta);
+                            w = cfmac(x, make_float2(g * e.x, g * e.y), w);
+                        } else {
+                            const float sx = wsum(cv * x2);
+                            psi = fmaf(prm.klam, psi, prm.koml * fmaf(e.x, e.x, e.y * e.y));
+                            const float d = sx + psi + prm.keps;
+                            const float r0 = rcp_fast(d);
+                            const float rd = fmaf(r0, -fmaf(d, r0, -1.f), r0);
+                            const float gs = cv * rd;
+                            w = cfma(make_float2(gs * x.x, -gs * x.y), e, w);
+                            w = make_float2(prm.ka * w.x, prm.ka * w.y);
+                            cv = fmaf(prm.ka2 * (1.f - gs * x2), cv, prm.kq * fmaf(w.x, w.x, w.y * w.y));
+                        }
+                        if (lane == 0) {
+                            midE[2 * tl] = e;
+                            midE[2 * tl + 1] = yh;
+                        }
                     }
                 }
-            }
+            };
+            if (tc0 + F <= T) run(std::false_type{});
+            else run(std::true_type{});
             if (tap) {
                 midW[pl] = w;
                 if constexpr (ALGO == kAlgoKalman) midC[pl] = cv;
