@@ -330,8 +330,10 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
         minb = cfg->variant % 1000;
     } else {
         // measured defaults: short filters 2 warps / 2 pairs per thread; 8 partitions and
-        // more: 8 warps, one bin per thread (16-partition NLMS: 4 warps, one pair per thread)
-        nw = (P <= 4) ? 2 : (P >= 16 && cfg->algo == AEC_ALGO_NLMS) ? 4 : 8;
+        // more: 8 warps, one bin per thread (since bin 128 of the ring kernels runs one chunk ahead on the idle
+        // synthesis warps this also holds for the 16-partition NLMS filter: 5.71 ms per 2048 x 10 s against 5.95
+        // for the 4-warp / 255-register kernel, which remains available as variant 4255)
+        nw = (P <= 4) ? 2 : 8;
         // (defaults: the first instantiation listed for (P, algo, echo) in stage1_inst_nw*.cu --
         //  128 registers for the two-warp kernels so that 7 utterances stay resident per SM)
     }
