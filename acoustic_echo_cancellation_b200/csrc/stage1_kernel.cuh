@@ -524,17 +524,42 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     q[2 * j + sig] = (lane & 1) ? b2 : -b2;
                 }
             }
+            // eight sums over the 32 lanes in 9 shuffles instead of 40 (the shuffle unit is shared by the SM and was the
+            // longest part of this step): at every level a lane keeps half of its values and hands the other half to its
+            // partner; after three levels it owns one value, two more levels finish it.  The value a lane ends up with:
+            // bit 4 of the lane selects q over r, bit 3 the frame (j), bit 2 the signal.
+            float v8[8] = {r[0], r[1], r[2], r[3], q[0], q[1], q[2], q[3]};    // index = 4 * (q ? 1 : 0) + 2 * j + sig
+            float v4[4], v2[2], v1;
+            {
+                const bool up = lane & 16;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    r[v] += __shfl_xor_sync(0xffffffffu, r[v], o);
-                    q[v] += __shfl_xor_sync(0xffffffffu, q[v], o);
+                for (int k = 0; k < 4; ++k) {
+                    const float mine = up ? v8[4 + k] : v8[k], other = up ? v8[k] : v8[4 + k];
+                    v4[k] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
                 }
             }
-            if (lane < 2 && tc0 + tl0 + lane < T) {                // (the table carries the 1/2)
-                midH[P + tl0 + lane] = lane == 0 ? make_float2(2.f * r[0], 2.f * q[0]) : make_float2(2.f * r[2], 2.f * q[2]);
-                midY[tl0 + lane] = lane == 0 ? make_float2(2.f * r[1], 2.f * q[1]) : make_float2(2.f * r[3], 2.f * q[3]);
+            {
+                const bool up = lane & 8;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float mine = up ? v4[2 + k] : v4[k], other = up ? v4[k] : v4[2 + k];
+                    v2[k] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+                }
+            }
+            {
+                const bool up = lane & 4;
+                const float mine = up ? v2[1] : v2[0], other = up ? v2[0] : v2[1];
+                v1 = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+            }
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            // lane 4 * i holds value i: [r: (j0 far, j0 mic, j1 far, j1 mic)] in lanes 0, 4, 8, 12, [q: ...] in 16 .. 28
+            {
+                const int j = (lane >> 3) & 1, sig = (lane >> 2) & 1, isq = lane >> 4;
+                if ((lane & 3) == 0 && tc0 + tl0 + j < T) {            // (the table carries the 1/2)
+                    float* dstf = reinterpret_cast<float*>(sig == 0 ? midH + P + tl0 + j : midY + tl0 + j);
+                    dstf[isq] = 2.f * v1;
+                }
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"((NW - F / 2) * 32) : "memory");     // warps F/2 .. NW-1 only
