@@ -250,7 +250,8 @@ __device__ __forceinline__ void pack_pair(float2 ek, float2 em, float2 w, float2
     gm = make_float2(a.x + t.y, t.x - a.y);
 }
 
-constexpr int kRingPitch = 264;   // far-end history ring: float2 per slot (257 bins, padded)
+constexpr int kRingPitch = 256;   // far-end history ring: one float2 column per thread and slot (bin 128 has its own history);
+                                  // a power of two, so that a slot offset is a shift instead of an integer multiply
 
 template <int NW, int P>
 struct Stage1Smem {
@@ -721,7 +722,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     const float2 xn = unpack1(fo, fx);
                     if constexpr (kRing) {
                         const int tt = t0 + tl;
-                        float2* col = xring + k_bin;
+                        float2* col = xring + tid;       // (any one-to-one column assignment: a thread reads back its own)
 #pragma unroll
                         for (int p = 1; p < P; ++p) st[0].X[p] = col[((tt - p) & (P - 1)) * kRingPitch];
                         col[(tt & (P - 1)) * kRingPitch] = xn;
