@@ -70,6 +70,34 @@ def main():
                          "istft": float((istft(s_ours) - ref_istft(s_ours)).abs().max()),
                          "features": float((A.stage2_features(x, y, erb, in_norm=False) - ref_feat(x, y)).abs().max())},
     }
+    # ---- Stage-2 inference (Little_net.forward, ERB.py:252-316) restated with torch modules (cuDNN GRU) ----
+    torch.manual_seed(0)
+    gru = torch.nn.GRU(64, 32, batch_first=True).cuda().eval()
+    lin1, lin2 = torch.nn.Linear(64, 32).cuda().eval(), torch.nn.Linear(32, 32).cuda().eval()
+    sd = {"gru1.weight_ih_l0": gru.weight_ih_l0, "gru1.weight_hh_l0": gru.weight_hh_l0, "gru1.bias_ih_l0": gru.bias_ih_l0,
+          "gru1.bias_hh_l0": gru.bias_hh_l0, "linear1.weight": lin1.weight, "linear1.bias": lin1.bias,
+          "linear2.weight": lin2.weight, "linear2.bias": lin2.bias}
+    net = A.LittleNetInference({k: v.detach() for k, v in sd.items()}, erb)
+
+    @torch.no_grad()
+    def ref_stage2(m, r):
+        m = m - m.mean() / m.std()
+        r = r - r.mean() / r.std()
+        sm, sr = ref_stft(m), ref_stft(r)
+        mm = torch.sqrt(sm[:, :257] ** 2 + sm[:, 257:] ** 2 + 1e-9).transpose(1, 2) @ erb
+        mr = torch.sqrt(sr[:, :257] ** 2 + sr[:, 257:] ** 2 + 1e-9).transpose(1, 2) @ erb
+        feat = torch.cat([mm, (mm - mr).abs()], 2)
+        o1, _ = gru(feat)
+        mask = torch.sigmoid(lin2(torch.relu(lin1(torch.cat([o1, mm], 2)))))
+        gain = ((mask * mm) @ erb.T).transpose(1, 2)
+        est = torch.cat([gain * sm[:, :257], gain * sm[:, 257:]], 1)
+        return ref_istft(est).squeeze(1) + 1e-9
+
+    o_ours, o_ref = net(x, y), ref_stage2(x, y)
+    res["stage2_inference_ms"] = {"ours": timeit(lambda: net(x, y), 5), "torch_cudnn_restatement": timeit(lambda: ref_stage2(x, y), 5)}
+    n_cmp = min(o_ours.shape[1], o_ref.shape[1])
+    res["max_abs_diff"]["stage2"] = float((o_ours[:, :n_cmp] - o_ref[:, :n_cmp]).abs().max())
+    res["stage2_out_scale"] = float(o_ref.abs().max())
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/ops_bench.json", "w"), indent=1)
