@@ -5,6 +5,7 @@
 // The feature tensor fed to the GRU comes from aec_features (ERB.py:262-290).  Pinned by
 // tests/golden/reference_stage2.npz (the reference module itself, seeded weights).
 #include <cstdint>
+#include <type_traits>
 
 #include "aec_common.cuh"
 #include "fft_warp.cuh"
@@ -14,13 +15,16 @@ namespace {
 
 constexpr int kH = 32;          // hidden units == ERB bands (Little_net: GRU(2*bands -> bands))
 constexpr int kIn = 64;         // 2 * bands
-constexpr int kMaskWarps = 4;   // utterances per CTA
+// utterances (= warps) per CTA: 4 for large batches (the 45 KB of weights are staged once per CTA), 1 for batches that would
+// otherwise leave SMs empty -- the recurrence streams ~400 shared-memory wavefronts per utterance per frame, and four
+// utterances on one SM pay them one after the other while other SMs sit idle
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
 // One warp per utterance, lane j = hidden unit / band j.  Weights are staged transposed in shared
-// memory ([input][unit]: a warp reads 32 consecutive floats, conflict-free); the frame's feature
+// memory (groups of four inputs per unit, 16-byte loads); the frame's feature
 // vector and the hidden state are broadcast through a per-warp scratch.
+template <int kMaskWarps>
 __global__ void __launch_bounds__(kMaskWarps * 32) stage2_mask_kernel(const float* __restrict__ feat,
                                                                       aec_stage2_weights w, float* __restrict__ est,
                                                                       long long B, long long T) {
@@ -32,10 +36,25 @@ __global__ void __launch_bounds__(kMaskWarps * 32) stage2_mask_kernel(const floa
     float* bias = w2 + kH * kH;            // b_ih[96] b_hh[96] b1[32] b2[32]
     float* scratch = bias + 256;           // per warp: x[64] h[32] o2[32]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 96 * kIn; i += blockDim.x) wih[(i % kIn) * 96 + i / kIn] = __ldg(w.gru_w_ih + i);
-    for (int i = tid; i < 96 * kH; i += blockDim.x) whh[(i % kH) * 96 + i / kH] = __ldg(w.gru_w_hh + i);
-    for (int i = tid; i < kH * kIn; i += blockDim.x) w1[(i % kIn) * kH + i / kIn] = __ldg(w.lin1_w + i);
-    for (int i = tid; i < kH * kH; i += blockDim.x) w2[(i % kH) * kH + i / kH] = __ldg(w.lin2_w + i);
+    // weights as float4 groups of four consecutive inputs per (gate, unit): one 16-byte load feeds four FFMAs
+    //   wih : [gate 3][input/4 16][unit 32][4]     whh : [gate 3][input/4 8][unit 32][4]
+    //   w1  : [input/4 16][unit 32][4]             w2  : [input/4 8][unit 32][4]
+    for (int i = tid; i < 96 * kIn; i += blockDim.x) {
+        const int row = i / kIn, col = i % kIn, g = row >> 5, j = row & 31;
+        wih[(((g * (kIn / 4) + (col >> 2)) * 32 + j) << 2) + (col & 3)] = __ldg(w.gru_w_ih + i);
+    }
+    for (int i = tid; i < 96 * kH; i += blockDim.x) {
+        const int row = i / kH, col = i % kH, g = row >> 5, j = row & 31;
+        whh[(((g * (kH / 4) + (col >> 2)) * 32 + j) << 2) + (col & 3)] = __ldg(w.gru_w_hh + i);
+    }
+    for (int i = tid; i < kH * kIn; i += blockDim.x) {
+        const int j = i / kIn, col = i % kIn;
+        w1[((((col >> 2)) * 32 + j) << 2) + (col & 3)] = __ldg(w.lin1_w + i);
+    }
+    for (int i = tid; i < kH * kH; i += blockDim.x) {
+        const int j = i / kH, col = i % kH;
+        w2[((((col >> 2)) * 32 + j) << 2) + (col & 3)] = __ldg(w.lin2_w + i);
+    }
     for (int i = tid; i < 96; i += blockDim.x) {
         bias[i] = __ldg(w.gru_b_ih + i);
         bias[96 + i] = __ldg(w.gru_b_hh + i);
@@ -68,60 +87,55 @@ __global__ void __launch_bounds__(kMaskWarps * 32) stage2_mask_kernel(const floa
             x0 = __ldg(fb + (t + 1) * kIn + lane);
             x1 = __ldg(fb + (t + 1) * kIn + 32 + lane);
         }
-        float ar = b_r, az = b_z, ain = b_in, ahn = b_hn;
+        // four partial sums per gate (one per position inside a group of four inputs): the recurrence is latency-bound
+        // on one warp, and a single accumulator per gate made every step a chain of 96 dependent FFMAs
+        float ar[4] = {b_r, 0.f, 0.f, 0.f}, az[4] = {b_z, 0.f, 0.f, 0.f}, ain[4] = {b_in, 0.f, 0.f, 0.f},
+              ahn[4] = {b_hn, 0.f, 0.f, 0.f};
+        const float4* wih4 = reinterpret_cast<const float4*>(wih) + lane;
+        const float4* whh4 = reinterpret_cast<const float4*>(whh) + lane;
 #pragma unroll 4
-        for (int i = 0; i < kIn; i += 4) {
-            const float4 xv = *reinterpret_cast<const float4*>(xs + i);
-            const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float* row = wih + (i + u) * 96 + lane;
-                ar = fmaf(row[0], xa[u], ar);
-                az = fmaf(row[32], xa[u], az);
-                ain = fmaf(row[64], xa[u], ain);
-            }
+        for (int i4 = 0; i4 < kIn / 4; ++i4) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + 4 * i4);
+            const float4 wr = wih4[(0 * (kIn / 4) + i4) * 32], wz = wih4[(1 * (kIn / 4) + i4) * 32], wn = wih4[(2 * (kIn / 4) + i4) * 32];
+            ar[0] = fmaf(wr.x, xv.x, ar[0]); ar[1] = fmaf(wr.y, xv.y, ar[1]); ar[2] = fmaf(wr.z, xv.z, ar[2]); ar[3] = fmaf(wr.w, xv.w, ar[3]);
+            az[0] = fmaf(wz.x, xv.x, az[0]); az[1] = fmaf(wz.y, xv.y, az[1]); az[2] = fmaf(wz.z, xv.z, az[2]); az[3] = fmaf(wz.w, xv.w, az[3]);
+            ain[0] = fmaf(wn.x, xv.x, ain[0]); ain[1] = fmaf(wn.y, xv.y, ain[1]); ain[2] = fmaf(wn.z, xv.z, ain[2]); ain[3] = fmaf(wn.w, xv.w, ain[3]);
         }
 #pragma unroll 4
-        for (int i = 0; i < kH; i += 4) {
-            const float4 hv = *reinterpret_cast<const float4*>(hs + i);
-            const float ha[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float* row = whh + (i + u) * 96 + lane;
-                ar = fmaf(row[0], ha[u], ar);
-                az = fmaf(row[32], ha[u], az);
-                ahn = fmaf(row[64], ha[u], ahn);
-            }
+        for (int i4 = 0; i4 < kH / 4; ++i4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hs + 4 * i4);
+            const float4 wr = whh4[(0 * (kH / 4) + i4) * 32], wz = whh4[(1 * (kH / 4) + i4) * 32], wn = whh4[(2 * (kH / 4) + i4) * 32];
+            ar[0] = fmaf(wr.x, hv.x, ar[0]); ar[1] = fmaf(wr.y, hv.y, ar[1]); ar[2] = fmaf(wr.z, hv.z, ar[2]); ar[3] = fmaf(wr.w, hv.w, ar[3]);
+            az[0] = fmaf(wz.x, hv.x, az[0]); az[1] = fmaf(wz.y, hv.y, az[1]); az[2] = fmaf(wz.z, hv.z, az[2]); az[3] = fmaf(wz.w, hv.w, az[3]);
+            ahn[0] = fmaf(wn.x, hv.x, ahn[0]); ahn[1] = fmaf(wn.y, hv.y, ahn[1]); ahn[2] = fmaf(wn.z, hv.z, ahn[2]); ahn[3] = fmaf(wn.w, hv.w, ahn[3]);
         }
-        const float r = sigmoidf_(ar), z = sigmoidf_(az);
-        const float n = tanhf(fmaf(r, ahn, ain));
+        const float r = sigmoidf_((ar[0] + ar[1]) + (ar[2] + ar[3])), z = sigmoidf_((az[0] + az[1]) + (az[2] + az[3]));
+        const float n = tanhf(fmaf(r, (ahn[0] + ahn[1]) + (ahn[2] + ahn[3]), (ain[0] + ain[1]) + (ain[2] + ain[3])));
         h = fmaf(z, h - n, n);                       // (1 - z) n + z h
         __syncwarp();
         hs[lane] = h;
         __syncwarp();
-        float a1 = b_1;                              // linear1 on cat[h, mic_erb]  (ERB.py:295-298)
+        float a1[4] = {b_1, 0.f, 0.f, 0.f}, a1x[4] = {0.f, 0.f, 0.f, 0.f};   // linear1 on cat[h, mic_erb]  (ERB.py:295-298)
+        const float4* w14 = reinterpret_cast<const float4*>(w1) + lane;
 #pragma unroll 4
-        for (int i = 0; i < kH; i += 4) {
-            const float4 hv = *reinterpret_cast<const float4*>(hs + i);
-            const float4 xv = *reinterpret_cast<const float4*>(xs + i);
-            const float ha[4] = {hv.x, hv.y, hv.z, hv.w}, xa[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                a1 = fmaf(w1[(i + u) * kH + lane], ha[u], a1);
-                a1 = fmaf(w1[(kH + i + u) * kH + lane], xa[u], a1);
-            }
+        for (int i4 = 0; i4 < kH / 4; ++i4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hs + 4 * i4);
+            const float4 xv = *reinterpret_cast<const float4*>(xs + 4 * i4);
+            const float4 wa = w14[i4 * 32], wb = w14[(kH / 4 + i4) * 32];      // inputs 0..31 = h, 32..63 = mic_erb
+            a1[0] = fmaf(wa.x, hv.x, a1[0]); a1[1] = fmaf(wa.y, hv.y, a1[1]); a1[2] = fmaf(wa.z, hv.z, a1[2]); a1[3] = fmaf(wa.w, hv.w, a1[3]);
+            a1x[0] = fmaf(wb.x, xv.x, a1x[0]); a1x[1] = fmaf(wb.y, xv.y, a1x[1]); a1x[2] = fmaf(wb.z, xv.z, a1x[2]); a1x[3] = fmaf(wb.w, xv.w, a1x[3]);
         }
-        os[lane] = fmaxf(a1, 0.f);
+        os[lane] = fmaxf(((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1x[0] + a1x[1]) + (a1x[2] + a1x[3])), 0.f);
         __syncwarp();
-        float a2 = b_2;                              // linear2 + sigmoid  (ERB.py:301)
+        float a2[4] = {b_2, 0.f, 0.f, 0.f};          // linear2 + sigmoid  (ERB.py:301)
+        const float4* w24 = reinterpret_cast<const float4*>(w2) + lane;
 #pragma unroll 4
-        for (int i = 0; i < kH; i += 4) {
-            const float4 ov = *reinterpret_cast<const float4*>(os + i);
-            const float oa[4] = {ov.x, ov.y, ov.z, ov.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) a2 = fmaf(w2[(i + u) * kH + lane], oa[u], a2);
+        for (int i4 = 0; i4 < kH / 4; ++i4) {
+            const float4 ov = *reinterpret_cast<const float4*>(os + 4 * i4);
+            const float4 wv = w24[i4 * 32];
+            a2[0] = fmaf(wv.x, ov.x, a2[0]); a2[1] = fmaf(wv.y, ov.y, a2[1]); a2[2] = fmaf(wv.z, ov.z, a2[2]); a2[3] = fmaf(wv.w, ov.w, a2[3]);
         }
-        eb[t * kH + lane] = sigmoidf_(a2) * merb;    // est_erb = mask * mic_erb  (ERB.py:304)
+        eb[t * kH + lane] = sigmoidf_((a2[0] + a2[1]) + (a2[2] + a2[3])) * merb;    // est_erb = mask * mic_erb  (ERB.py:304)
     }
 }
 
@@ -269,10 +283,19 @@ extern "C" int aec_stage2_mask(const float* feat, const aec_stage2_weights* w, f
     Tables tab;
     int rc = get_tables(&tab);                        // device check (sm_100 only)
     if (rc != AEC_OK) return rc;
-    const size_t smem = (size_t)(kIn * 96 + kH * 96 + kIn * kH + kH * kH + 256 + kMaskWarps * 128) * sizeof(float);
-    AEC_CUDA_CHECK(cudaFuncSetAttribute(stage2_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((B + kMaskWarps - 1) / kMaskWarps);
-    stage2_mask_kernel<<<grid, kMaskWarps * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(feat, *w, est_erb, B, T);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto launch = [&](auto warps_tag) -> int {
+        constexpr int kW = decltype(warps_tag)::value;
+        const size_t smem = (size_t)(kIn * 96 + kH * 96 + kIn * kH + kH * kH + 256 + kW * 128) * sizeof(float);
+        AEC_CUDA_CHECK(cudaFuncSetAttribute(stage2_mask_kernel<kW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)((B + kW - 1) / kW);
+        stage2_mask_kernel<kW><<<grid, kW * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(feat, *w, est_erb, B, T);
+        return AEC_OK;
+    };
+    rc = (B <= 4LL * sms) ? launch(std::integral_constant<int, 1>{}) : launch(std::integral_constant<int, 4>{});
+    if (rc != AEC_OK) return rc;
     AEC_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return AEC_OK;
