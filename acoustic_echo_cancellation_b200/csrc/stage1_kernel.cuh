@@ -19,7 +19,13 @@
 //                       overlap with one shuffle and the cross-warp overlap through 1 KB
 //                       tails in shared memory, and streams the error signal to HBM.
 // Far-end / microphone hops are staged HBM -> shared memory by the bulk-copy engine (TMA,
-// cp.async.bulk + mbarrier) one chunk ahead of the analysis phase; spectra never touch HBM.
+// cp.async.bulk + mbarrier) one chunk ahead of the analysis phase -- one or two copies per signal
+// per chunk, issued by an elected lane; spectra never touch HBM.
+// Bin 128 (its own mirror, the 257th bin on 256 bin slots) is a serial pass: on one lane inside the
+// frame loop for short filters (owner warp alternating with the hardware warp slot), and one chunk
+// AHEAD on the warps without synthesis work for the 16-partition ring kernels, where X[128], Y[128]
+// are evaluated directly from the staged samples ((-i)^n sums, no FFT).  Measurements and the
+// reasons for every one of these choices: DESIGN.md section 5, profiles/.
 #pragma once
 #include <cstdint>
 #include <type_traits>
