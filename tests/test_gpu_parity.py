@@ -204,6 +204,27 @@ def test_full_occupancy_runs_are_bitwise_repeatable(P, algo, B):
     assert torch.equal(alone[0], ref[0][b])
 
 
+def test_wav2h5_runner_pcm16_and_tapered_slices_match_the_device_path():
+    """The generator's runner (host pipeline, echo output on) on a batch that exercises the tapered last slices
+    (300 utterances in slices of 64: 64 x 4, 22, 11, 11) gives the device path's results, and the int16 PCM form of the
+    same signals (what create_h5 sends for a 16-bit wav corpus) gives bit-identical ones."""
+    from acoustic_echo_cancellation_b200 import wav2h5
+    B, L = 300, 2048 + 100
+    rng = np.random.default_rng(3)
+    pcm_f = rng.integers(-6000, 6000, size=(B, L), dtype=np.int16)
+    pcm_m = np.roll(pcm_f, 7, axis=1) // 2
+    far, mic = pcm_f.astype(np.float32) / 32768.0, pcm_m.astype(np.float32) / 32768.0
+    n = np.full(B, L, dtype=np.int64)
+    n[5], n[77] = 900, 257
+    run = wav2h5.default_runner(slice_utterances=64)
+    err_f, echo_f = run(far, mic, n)
+    err_p, echo_p = run(pcm_f, pcm_m, n)
+    assert err_f.dtype == np.float32 and err_p.dtype == np.float32
+    assert np.array_equal(err_f, err_p) and np.array_equal(echo_f, echo_p)
+    dev = A.stage1_aec(_cuda(far), _cuda(mic), A.Stage1Config(), n_samples=_cuda(n), return_echo=True)
+    assert np.array_equal(err_f, dev[0].cpu().numpy()) and np.array_equal(echo_f, dev[1].cpu().numpy())
+
+
 def test_host_buffer_entry_matches_device_entry():
     L, B = 16000, 10
     d = synth.make_batch(0, B, L)

@@ -117,7 +117,11 @@ def test_create_h5_train_and_test_schema(tmp_path):
     for d in (wav_dir, h5_dir, list_dir):
         d.mkdir()
     _write_wavs(str(wav_dir), ["3", "11"])
-    runner = lambda fa, mi, n: (fa * 0.5, mi * 0.25)          # noqa: E731  (stand-in for the CUDA runner)
+    def runner(fa, mi, n):            # stand-in for the CUDA runner: like the C ABI it takes float32 or 16-bit PCM
+        if fa.dtype == np.int16:      # (the test wavs are 16-bit, so this is the branch create_h5 takes)
+            fa, mi = fa.astype(np.float32) / np.float32(32768), mi.astype(np.float32) / np.float32(32768)
+        return fa * np.float32(0.5), mi * np.float32(0.25)
+
     fake = _FakeH5()
     args = types.SimpleNamespace(train_path=str(wav_dir), h5_path=str(h5_dir), list_path=str(list_dir), sr=16000)
     paths = wav2h5.create_h5_train(args, runner=runner, batch=1, h5=fake)
@@ -151,3 +155,26 @@ def test_cpulist_parser_and_bind_is_harmless_without_gpu():
     assert hostutil._parse_cpulist("") == []
     if not torch.cuda.is_available():
         assert hostutil.gpu_local_cpus(0) is None and hostutil.bind_to_gpu_numa(0) is None
+
+
+def test_stage1_batch_sends_exact_pcm16_as_int16_and_everything_else_as_float32():
+    rng = np.random.default_rng(0)
+    pcm = [rng.integers(-32768, 32768, size=n, dtype=np.int16) for n in (700, 512)]
+    far = [p.astype(np.float32) / 32768.0 for p in pcm]            # what librosa.load returns for a 16-bit wav
+    mic = [np.roll(f, 3) for f in far]
+    seen = {}
+
+    def runner(fa, mi, n):
+        seen["dtype"], seen["far"], seen["n"] = fa.dtype, fa.copy(), n.copy()
+        z = np.zeros(fa.shape, dtype=np.float32)
+        return z, z
+
+    errs, _ = wav2h5._stage1_batch(far, mic, runner)
+    assert seen["dtype"] == np.int16 and [len(e) for e in errs] == [700, 512]
+    assert np.array_equal(seen["far"][0, :700], pcm[0]) and np.array_equal(seen["far"][1, :512], pcm[1])
+    assert (seen["far"][1, 512:] == 0).all()
+    far[1] = far[1] + np.float32(1e-6)                             # not representable as PCM16 any more
+    wav2h5._stage1_batch(far, mic, runner)
+    assert seen["dtype"] == np.float32
+    assert wav2h5.as_pcm16(np.array([1.0], dtype=np.float32)) is None          # +1.0 would be 32768: out of range
+    assert wav2h5.as_pcm16(np.array([-1.0, 0.5], dtype=np.float32)).tolist() == [-32768, 16384]
