@@ -1,6 +1,8 @@
 """Generate golden vectors by IMPORTING THE REFERENCE (run in the build container only).
 
     python tests/golden/make_golden.py            # writes tests/golden/reference_ops.npz
+    python tests/golden/make_golden.py stage2     # writes tests/golden/reference_stage2.npz (Little_net, seeded weights)
+    python tests/golden/make_golden.py full       # writes tests/golden/reference_full_size.npz (10 s summaries)
 
 The reference (SZU-Speech/Acoustic-Echo-Cancellation, mounted read-only at
 /root/reference) has no tests and no fixtures, so the golden vectors are outputs
@@ -31,6 +33,8 @@ from network.ERB import EquivalentRectangularBandwidth  # noqa: E402
 from utils.tools import countFrames  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from fullsize import full_size_inputs, full_size_positions  # noqa: E402
 
 
 def main():
@@ -133,8 +137,66 @@ def stage2_golden():
     print("wrote", path, os.path.getsize(path), "bytes;", sorted(out))
 
 
+def full_size_golden():
+    """BASELINE.json's utterance length (10 s, 16 kHz) through the reference's own operators and its live model:
+    the outputs are too large to commit, so tests/golden/reference_full_size.npz keeps 256 single values at fixed
+    positions plus per-channel / per-frame sums of each output (float64) -- enough to catch a wrong frame count,
+    layout, window, normalisation or band anywhere in the 626 frames."""
+    from network.ERB import Little_net
+
+    torch.set_num_threads(4)
+    mic, ref = full_size_inputs()
+    stft = ConvSTFT(512, 256, 512, "hann", "complex", fix=True)
+    istft = ConviSTFT(512, 256, 512, "hann", "complex", fix=True)
+    erb = EquivalentRectangularBandwidth(257, 16000, 32, 0, 8000).filters
+    out = {}
+    with torch.no_grad():
+        s = stft(torch.from_numpy(mic))                                   # [2, 514, 626]
+        y = istft(s)                                                      # [2, 1, 160000]
+        s_np, y_np = s.numpy(), y.numpy()
+        out["stft_shape"], out["istft_shape"] = np.array(s_np.shape), np.array(y_np.shape)
+        out["stft_vals"] = s_np.ravel()[full_size_positions(s_np.shape)]
+        out["stft_sum_t"] = s_np.astype(np.float64).sum(axis=2)           # [2, 514]
+        out["stft_pow_c"] = (s_np.astype(np.float64) ** 2).sum(axis=1)    # [2, 626]
+        out["istft_vals"] = y_np.ravel()[full_size_positions(y_np.shape)]
+        out["istft_pow"] = (y_np.astype(np.float64) ** 2).sum(axis=(1, 2))
+        # feature front end (ERB.py:254-290), restated with the reference's modules as in main()
+        m_t, r_t = torch.from_numpy(mic), torch.from_numpy(ref)
+        m_t = m_t - m_t.mean() / m_t.std()
+        r_t = r_t - r_t.mean() / r_t.std()
+        feats = []
+        for v in (m_t, r_t):
+            sp = stft(v)
+            mag = torch.sqrt(sp[:, :257] ** 2 + sp[:, 257:] ** 2 + 1e-9).transpose(1, 2)
+            feats.append(mag @ torch.from_numpy(erb).float())
+        f_np = torch.cat([feats[0], (feats[0] - feats[1]).abs()], 2).numpy()          # [2, 626, 64]
+        out["feat_shape"] = np.array(f_np.shape)
+        out["feat_vals"] = f_np.ravel()[full_size_positions(f_np.shape)]
+        out["feat_sum_t"] = f_np.astype(np.float64).sum(axis=1)                         # [2, 64]
+        # the live model with the seeded weights of reference_stage2.npz
+        g = np.load(os.path.join(HERE, "reference_stage2.npz"))
+        net = Little_net({"win_size": 512, "hop_size": 256}, 32).eval()
+        sd = net.state_dict()
+        for k in list(sd):
+            key = "w_" + k.replace(".", "_")
+            if key in g.files:
+                sd[k] = torch.from_numpy(g[key])
+        net.load_state_dict(sd)
+        near = torch.zeros_like(m_t)
+        o, _ = net(torch.from_numpy(mic), torch.from_numpy(ref), near, torch.from_numpy(erb).float())
+        o_np = o.numpy()
+        out["net_shape"] = np.array(o_np.shape)
+        out["net_vals"] = o_np.ravel()[full_size_positions(o_np.shape)]
+        out["net_pow"] = (o_np.astype(np.float64) ** 2).sum(axis=-1).reshape(-1)
+    path = os.path.join(HERE, "reference_full_size.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "stage2":
         stage2_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "full":
+        full_size_golden()
     else:
         main()

@@ -329,6 +329,40 @@ def test_batches_larger_than_the_grid_y_limit():
     assert torch.equal(err[rows], A.stage1_aec(torch.roll(x, 3, dims=1)[rows].contiguous(), xs, A.Stage1Config(partitions=2)))
 
 
+def test_full_size_operators_against_reference_summaries():
+    """10 s utterances (BASELINE.json's length) through the stand-alone kernels and the Stage-2 inference kernels,
+    against 256 pinned values and per-channel / per-frame sums of the REFERENCE's own outputs
+    (tests/golden/reference_full_size.npz, written by tests/golden/make_golden.py full)."""
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, here)
+    from fullsize import full_size_inputs, full_size_positions
+    g = np.load(os.path.join(here, "reference_full_size.npz"))
+    mic, ref = full_size_inputs()
+
+    def check(name, arr, tol, sums=()):
+        assert list(arr.shape) == list(g[name + "_shape"])
+        want = g[name + "_vals"]
+        got = arr.ravel()[full_size_positions(arr.shape)]
+        assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max())
+        for key, fn in sums:
+            assert np.abs(fn(arr.astype(np.float64)) - g[key]).max() <= 1e-4 * max(1.0, np.abs(g[key]).max())
+
+    tm, tr = _cuda(mic), _cuda(ref)
+    s = A.ConvSTFT(512, 256, 512, "hann", "complex")(tm)
+    check("stft", s.cpu().numpy(), 2e-5, [("stft_sum_t", lambda a: a.sum(axis=2)), ("stft_pow_c", lambda a: (a ** 2).sum(axis=1))])
+    y = A.ConviSTFT(512, 256, 512, "hann", "complex")(s)
+    check("istft", y.cpu().numpy(), 2e-5, [("istft_pow", lambda a: (a ** 2).sum(axis=(1, 2)))])
+    erb = torch.from_numpy(O.erb_filterbank()).float().cuda()
+    f = A.stage2_features(tm, tr, erb)
+    check("feat", f.cpu().numpy(), 2e-4, [("feat_sum_t", lambda a: a.sum(axis=1))])
+    w = np.load(os.path.join(here, "reference_stage2.npz"))
+    net = A.LittleNetInference({k[2:]: w[k] for k in w.files if k.startswith("w_")}, w["erb"])
+    o = net(tm, tr)
+    check("net", o.cpu().numpy(), 3e-4, [("net_pow", lambda a: (a ** 2).sum(axis=-1).reshape(-1))])
+
+
 def test_stft_3d_input_and_ctor_errors():
     x = torch.randn(2, 1, 2048, device="cuda")
     s = A.ConvSTFT(512, 256, 512, "hann", "complex")(x)

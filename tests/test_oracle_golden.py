@@ -63,3 +63,43 @@ def test_stage2_little_net_inference_matches_reference_module():
     out = O.stage2_little_net(g["mic"], g["ref"], g["erb"], w)
     assert out.shape == g["out_wav"].shape
     assert np.abs(out - g["out_wav"]).max() < 2e-4 * max(1.0, np.abs(g["out_wav"]).max())
+
+
+# ---- BASELINE.json's utterance length (10 s) against summaries of the reference's own outputs -------------------
+def _full():
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, here)
+    from fullsize import full_size_inputs, full_size_positions
+    return np.load(os.path.join(here, "reference_full_size.npz")), full_size_inputs, full_size_positions
+
+
+def _check_summary(name, arr, g, pos_fn, tol_val, sums=()):
+    assert list(arr.shape) == list(g[name + "_shape"])
+    ref = g[name + "_vals"]
+    got = arr.ravel()[pos_fn(arr.shape)]
+    assert np.abs(got - ref).max() <= tol_val * max(1.0, np.abs(ref).max())
+    for key, fn in sums:
+        r = g[key]
+        assert np.abs(fn(arr.astype(np.float64)) - r).max() <= 1e-4 * max(1.0, np.abs(r).max())
+
+
+def test_full_size_stft_istft_features_against_reference_summaries():
+    g, inputs, pos = _full()
+    mic, ref = inputs()
+    s = O.stft(mic)                                                        # [2, 514, 626]
+    _check_summary("stft", s, g, pos, 2e-5, [("stft_sum_t", lambda a: a.sum(axis=2)), ("stft_pow_c", lambda a: (a ** 2).sum(axis=1))])
+    y = O.istft(s)
+    _check_summary("istft", y.reshape(g["istft_shape"]), g, pos, 2e-5, [("istft_pow", lambda a: (a ** 2).sum(axis=(1, 2)))])
+    f = O.stage2_features(mic, ref, O.erb_filterbank())
+    _check_summary("feat", f, g, pos, 2e-4, [("feat_sum_t", lambda a: a.sum(axis=1))])
+
+
+def test_full_size_little_net_against_reference_summary():
+    import os
+    g, inputs, pos = _full()
+    mic, ref = inputs()
+    w = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_stage2.npz"))
+    out = O.stage2_little_net(mic, ref, O.erb_filterbank(), {k[2:]: w[k] for k in w.files if k.startswith("w_")})
+    _check_summary("net", out, g, pos, 3e-4, [("net_pow", lambda a: (a ** 2).sum(axis=-1).reshape(-1))])
