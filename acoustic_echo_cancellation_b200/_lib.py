@@ -58,16 +58,20 @@ SIGNATURES = {
     "aec_version": (C.c_int, []),
     "aec_strerror": (C.c_char_p, [C.c_int]),
     "aec_last_cuda_error": (C.c_char_p, []),
+    "aec_init": (C.c_int, []),
     "aec_cfg_default": (C.c_int, [C.POINTER(AecCfg), _I32]),
     "aec_num_frames": (_I64, [_I64, _I32]),
     "aec_out_samples": (_I64, [_I64, _I32]),
     "aec_stage1_run": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, C.POINTER(AecCfg), _P]),
     "aec_host_ctx_create": (C.c_int, [C.POINTER(_P), _I64, _I64]),
+    "aec_host_ctx_create_ex": (C.c_int, [C.POINTER(_P), _I64, _I64, _I32, _I32]),
     "aec_host_ctx_destroy": (C.c_int, [_P]),
     "aec_stage1_run_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, C.POINTER(AecCfg)]),
     "aec_stage1_run_host_pcm16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, C.POINTER(AecCfg)]),
     "aec_host_alloc": (C.c_int, [C.POINTER(_P), _I64]),
+    "aec_host_alloc_ex": (C.c_int, [C.POINTER(_P), _I64, _I32]),
     "aec_host_free": (C.c_int, [_P]),
+    "aec_host_is_pinned": (C.c_int, [_P]),
     "aec_stft": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P]),
     "aec_istft": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P]),
     "aec_features": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I32, C.c_float, C.c_float, _P]),

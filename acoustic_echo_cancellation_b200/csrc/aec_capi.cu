@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "aec_common.cuh"
@@ -98,9 +99,15 @@ int build_tables(DeviceTables* dt) {
     char* dev = nullptr;
     AEC_CUDA_CHECK(cudaMalloc(&dev, 32768));
     size_t off = 0;
+    // (a private blocking-free stream: the legacy default stream would synchronise with -- or, under stream
+    //  capture, invalidate -- whatever the caller has in flight; call aec_init() before capturing a graph)
+    cudaStream_t ts = nullptr;
+    AEC_CUDA_CHECK(cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking));
+    cudaError_t put_err = cudaSuccess;
     auto put = [&](const void* src, size_t n) -> const void* {
         void* dst = dev + off;
-        cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+        const cudaError_t pe = cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ts);
+        if (put_err == cudaSuccess) put_err = pe;
         off += (n + 255) / 256 * 256;
         return dst;
     };
@@ -114,7 +121,13 @@ int build_tables(DeviceTables* dt) {
     dt->t.tw1024 = (const float2*)put(tw1024.data(), tw1024.size() * sizeof(float2));
     dt->t.win_a1k = (const float2*)put(win_a1k.data(), win_a1k.size() * sizeof(float2));
     dt->t.win_s1k = (const float2*)put(win_s1k.data(), win_s1k.size() * sizeof(float2));
-    AEC_CUDA_CHECK(cudaGetLastError());
+    if (put_err == cudaSuccess) put_err = cudaStreamSynchronize(ts);    // the host vectors die with this scope
+    (void)cudaStreamDestroy(ts);
+    if (put_err != cudaSuccess) {
+        set_cuda_error(put_err, "constant tables upload");
+        (void)cudaFree(dev);
+        return AEC_ECUDA;
+    }
     dt->ready = true;
     return AEC_OK;
 }
@@ -197,6 +210,11 @@ using namespace aec;
 // plain helpers
 // ------------------------------------------------------------------------------------------
 extern "C" int aec_version(void) { return AEC_B200_VERSION; }
+
+extern "C" int aec_init(void) {
+    Tables t;
+    return get_tables(&t);
+}
 
 extern "C" const char* aec_strerror(int code) {
     switch (code) {
@@ -313,7 +331,7 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         p.num_sms = sms > 0 ? sms : 148;
-        p.stagger_ns = cfg->stagger_ns < 0 ? 0 : cfg->stagger_ns;
+        p.stagger_ns = cfg->stagger_ns < 0 ? 0 : cfg->stagger_ns;   // off unless a positive skew is asked for
     }
     const bool wide = cfg->frame == 1024;
     p.tw256 = wide ? tab.tw512w : tab.tw256;
@@ -348,10 +366,7 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
         case 8: e = launch_stage1_nw8(P, cfg->algo, echo, minb, p, s); break;
         default: return AEC_EUNSUPPORTED;
     }
-    if (e == cudaErrorInvalidValue) {
-        (void)cudaGetLastError();
-        return AEC_EUNSUPPORTED;
-    }
+    if (e == kNoInstance) return AEC_EUNSUPPORTED;     // (P, algo, echo, register cap) not instantiated -- nothing was launched
     if (e != cudaSuccess) {
         set_cuda_error(e, "stage1 kernel launch");
         return AEC_ECUDA;
@@ -361,55 +376,83 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 1, host buffers: H2D -> kernel -> D2H pipeline, kSlots slices in flight
+// stage 1, host buffers: H2D -> kernel -> D2H pipeline, several slices in flight
 // ------------------------------------------------------------------------------------------
-// Slices in flight.  Every slot is one stream running H2D -> kernel -> D2H for one slice; a slice of 64
-// utterances keeps the GPU busy for ~0.65 ms (the latency of one utterance) between copies of 0.75-1.5 ms
-// per direction, so two slots leave both DMA engines idle part of the time; four keep them saturated.
-constexpr int kSlots = 4;
+// Every slot is one stream running H2D -> kernel -> D2H for one slice; a slice of 64 utterances keeps the
+// GPU busy for ~0.65 ms (the latency of one utterance) between copies of 0.75-1.5 ms per direction, so two
+// slots leave both DMA engines idle part of the time; four keep them saturated (profiles/r2_pcie_floor.md).
+constexpr int kMaxSlots = 8;
+constexpr int kDefaultSlots = 4;
 
 struct aec_host_ctx {
     int device = 0;
+    int slots = kDefaultSlots;
+    int ramp = 1;            // taper the first slices as well as the last ones
     int64_t slice = 0;       // utterances per slice
     int64_t max_samples = 0;
     int64_t stride = 0;      // device row stride (multiple of 4 floats)
-    cudaStream_t stream[kSlots] = {};
-    float* d_far[kSlots] = {};
-    float* d_mic[kSlots] = {};
-    float* d_err[kSlots] = {};
-    float* d_echo[kSlots] = {};
-    float* d_erle[kSlots] = {};
-    long long* d_n[kSlots] = {};
-    int16_t* d_pcm[kSlots] = {};   // [2 signals][slice][stride] int16 staging (allocated on first use)
+    cudaStream_t stream[kMaxSlots] = {};
+    float* d_far[kMaxSlots] = {};
+    float* d_mic[kMaxSlots] = {};
+    float* d_err[kMaxSlots] = {};
+    float* d_echo[kMaxSlots] = {};     // allocated on the first call that asks for the echo estimate
+    float* d_erle[kMaxSlots] = {};
+    long long* d_n[kMaxSlots] = {};
+    int16_t* d_pcm[kMaxSlots] = {};    // [2 signals][slice][stride] int16 staging (allocated on first use)
     // page-locked staging for the small per-utterance arrays: a copy to / from pageable host memory
     // would serialise the multi-stream pipeline
-    float* h_erle[kSlots] = {};
-    long long* h_n[kSlots] = {};
-    int64_t pending_off[kSlots] = {-1, -1, -1, -1};        // slice whose ERLE still sits in h_erle[k]
-    int64_t pending_nb[kSlots] = {};
+    float* h_erle[kMaxSlots] = {};
+    long long* h_n[kMaxSlots] = {};
+    int64_t pending_off[kMaxSlots];    // slice whose ERLE still sits in h_erle[k] (-1: none)
+    int64_t pending_nb[kMaxSlots] = {};
+    aec_host_ctx() {
+        for (int i = 0; i < kMaxSlots; ++i) pending_off[i] = -1;
+    }
 };
 
-// Utterances of the next slice.  The upload engine is the bottleneck and stays busy to the end; what follows the last
-// upload (kernel: the 0.65 ms latency of one utterance, then its download) is pure tail, so the last slices are tapered
-// (.. 64, 32, 16, 16) to leave a small download behind the last kernel.
-static int64_t host_slice(int64_t slice, int64_t remaining) {
-    if (remaining > slice) return slice;          // (never more than the context's capacity)
+// Utterances of the next slice.  What precedes the first download (upload of the first slice, the 0.65 ms
+// latency of one utterance) and what follows the last upload (kernel, download) is pure ramp / tail, so the
+// first slices grow (16, 32, 64, ..) and the last ones shrink (.., 64, 32, 16, 16) around full-size slices.
+static int64_t host_slice(const aec_host_ctx* ctx, int64_t done, int64_t remaining) {
+    int64_t cap = ctx->slice;
+    if (ctx->ramp && remaining > 2 * ctx->slice) {
+        const int64_t grow = done < 16 ? 16 : done;           // 16, 16 -> 32, 32 -> 64, ...
+        if (grow < cap) cap = grow;
+    }
+    if (remaining > cap) return cap;              // (never more than the context's capacity)
     if (remaining <= 16) return remaining;
     return (remaining + 1) / 2;
 }
 
 // drain slot k: wait for its stream, hand the staged ERLE values to the caller
 static int host_ctx_drain(aec_host_ctx* ctx, int k, float* erle_db) {
-    AEC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream[k]));
-    if (erle_db && ctx->pending_off[k] >= 0)
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream[k]);
+    if (e == cudaSuccess && erle_db && ctx->pending_off[k] >= 0)
         memcpy(erle_db + ctx->pending_off[k], ctx->h_erle[k], (size_t)ctx->pending_nb[k] * sizeof(float));
     ctx->pending_off[k] = -1;
+    if (e != cudaSuccess) {
+        set_cuda_error(e, "aec_stage1_run_host: cudaStreamSynchronize");
+        return AEC_ECUDA;
+    }
     return AEC_OK;
+}
+
+// failure path: nothing of this call may still be in flight towards the caller's buffers when it returns,
+// and no stale ERLE slice may survive into the next call
+static void host_ctx_quiesce(aec_host_ctx* ctx) {
+    for (int i = 0; i < ctx->slots; ++i) {
+        if (ctx->stream[i]) (void)cudaStreamSynchronize(ctx->stream[i]);
+        ctx->pending_off[i] = -1;
+    }
+    (void)cudaGetLastError();
 }
 
 extern "C" int aec_host_ctx_destroy(aec_host_ctx* ctx) {
     if (!ctx) return AEC_OK;
-    for (int i = 0; i < kSlots; ++i) {
+    int prev = -1;
+    (void)cudaGetDevice(&prev);
+    (void)cudaSetDevice(ctx->device);
+    for (int i = 0; i < kMaxSlots; ++i) {
         if (ctx->stream[i]) cudaStreamSynchronize(ctx->stream[i]);
         cudaFree(ctx->d_far[i]);
         cudaFree(ctx->d_mic[i]);
@@ -422,25 +465,28 @@ extern "C" int aec_host_ctx_destroy(aec_host_ctx* ctx) {
         cudaFreeHost(ctx->h_n[i]);
         if (ctx->stream[i]) cudaStreamDestroy(ctx->stream[i]);
     }
+    if (prev >= 0) (void)cudaSetDevice(prev);
     delete ctx;
     return AEC_OK;
 }
 
-extern "C" int aec_host_ctx_create(aec_host_ctx** out, int64_t slice_utterances, int64_t max_samples) {
-    if (!out || slice_utterances <= 0 || max_samples <= 0) return AEC_EINVAL;
+extern "C" int aec_host_ctx_create_ex(aec_host_ctx** out, int64_t slice_utterances, int64_t max_samples, int32_t slots,
+                                      int32_t flags) {
+    if (!out || slice_utterances <= 0 || max_samples <= 0 || slots < 0 || slots > kMaxSlots) return AEC_EINVAL;
     aec_host_ctx* ctx = new (std::nothrow) aec_host_ctx();
     if (!ctx) return AEC_ENOMEM;
+    ctx->slots = slots == 0 ? kDefaultSlots : slots;
+    ctx->ramp = (flags & AEC_HOST_CTX_NO_RAMP) ? 0 : 1;
     ctx->slice = slice_utterances;
     ctx->max_samples = max_samples;
     ctx->stride = (max_samples + 3) / 4 * 4;
     cudaError_t e = cudaGetDevice(&ctx->device);
     const size_t sig = (size_t)ctx->slice * (size_t)ctx->stride * sizeof(float);
-    for (int i = 0; i < kSlots && e == cudaSuccess; ++i) {
+    for (int i = 0; i < ctx->slots && e == cudaSuccess; ++i) {
         e = cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_far[i], sig);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_mic[i], sig);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_err[i], sig);
-        if (e == cudaSuccess) e = cudaMalloc(&ctx->d_echo[i], sig);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_erle[i], (size_t)ctx->slice * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_n[i], (size_t)ctx->slice * sizeof(long long));
         if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_erle[i], (size_t)ctx->slice * sizeof(float), cudaHostAllocDefault);
@@ -449,172 +495,165 @@ extern "C" int aec_host_ctx_create(aec_host_ctx** out, int64_t slice_utterances,
     if (e != cudaSuccess) {
         set_cuda_error(e, "aec_host_ctx_create");
         aec_host_ctx_destroy(ctx);
+        (void)cudaGetLastError();
         return e == cudaErrorMemoryAllocation ? AEC_ENOMEM : AEC_ECUDA;
     }
     *out = ctx;
     return AEC_OK;
 }
 
-extern "C" int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const float* mic, float* err, float* echo_est,
-                                   float* erle_db, const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride,
-                                   int64_t out_stride, const aec_cfg* cfg) {
+extern "C" int aec_host_ctx_create(aec_host_ctx** out, int64_t slice_utterances, int64_t max_samples) {
+    return aec_host_ctx_create_ex(out, slice_utterances, max_samples, 0, 0);
+}
+
+namespace {
+// One body for both host entries: In = float (samples as librosa.load returns them) or int16_t (the PCM the wav
+// files hold; converted on the GPU).
+template <typename In>
+int run_host_impl(aec_host_ctx* ctx, const In* far, const In* mic, float* err, float* echo_est, float* erle_db,
+                  const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride, int64_t out_stride,
+                  const aec_cfg* cfg) {
+    constexpr bool kPcm = std::is_same<In, int16_t>::value;
     if (!ctx) return AEC_EINVAL;
     int rc = validate_cfg(cfg);
     if (rc != AEC_OK) return rc;
     if (B < 0 || L < 0 || L > ctx->max_samples || in_stride < L || out_stride < L) return AEC_EINVAL;
     if (B == 0) return AEC_OK;
     if (!far || !mic || !err) return AEC_EINVAL;
-    const size_t row = (size_t)L * sizeof(float);
-    const size_t dpitch = (size_t)ctx->stride * sizeof(float);
-    int first_rc = AEC_OK;
+    int dev = -1;
+    AEC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev != ctx->device) return AEC_EINVAL;     // the context's streams and buffers belong to ctx->device
+    const size_t sig_elems = (size_t)ctx->slice * (size_t)ctx->stride;     // elements per signal per slot
+    for (int i = 0; i < ctx->slots; ++i) {
+        if (echo_est && !ctx->d_echo[i]) AEC_CUDA_CHECK(cudaMalloc(&ctx->d_echo[i], sig_elems * sizeof(float)));
+        if (kPcm && !ctx->d_pcm[i]) AEC_CUDA_CHECK(cudaMalloc(&ctx->d_pcm[i], 2 * sig_elems * sizeof(int16_t)));
+    }
+    int sms = 148;
+    (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const size_t in_row = (size_t)L * sizeof(In), out_row = (size_t)L * sizeof(float);
+    const size_t in_spitch = (size_t)in_stride * sizeof(In), in_dpitch = (size_t)ctx->stride * sizeof(In);
+    const size_t out_pitch = (size_t)out_stride * sizeof(float), dpitch = (size_t)ctx->stride * sizeof(float);
+    // contiguous rows on both sides -> one linear copy per signal (the DMA engines run linear copies at full
+    // PCIe rate; pitched copies are only used for strided host layouts)
+    const bool lin_in = (in_stride == L) && (ctx->stride == L);
+    const bool lin_out = (out_stride == L) && (ctx->stride == L);
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) {
+        if (e == cudaSuccess && r != cudaSuccess) e = r;
+        return e == cudaSuccess;
+    };
     int64_t nb = 0;
-    for (int64_t off = 0, it = 0; off < B; off += nb, ++it) {
-        const int k = (int)(it % kSlots);
-        nb = host_slice(ctx->slice, B - off);
+    for (int64_t off = 0, it = 0; off < B && rc == AEC_OK && e == cudaSuccess; off += nb, ++it) {
+        const int k = (int)(it % ctx->slots);
+        nb = host_slice(ctx, off, B - off);
         cudaStream_t s = ctx->stream[k];
-        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (kSlots slices ago) is done
-        if (rc != AEC_OK) return rc;
-        // contiguous rows on both sides -> one linear copy per signal (the DMA engines run linear copies
-        // at full PCIe rate; pitched copies are only used for strided host layouts)
-        const bool lin_in = (in_stride == L) && (ctx->stride == L);
+        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (`slots` slices ago) is done
+        if (rc != AEC_OK) break;
+        In* up_f = kPcm ? reinterpret_cast<In*>(ctx->d_pcm[k]) : reinterpret_cast<In*>(ctx->d_far[k]);
+        In* up_m = kPcm ? reinterpret_cast<In*>(ctx->d_pcm[k]) + sig_elems : reinterpret_cast<In*>(ctx->d_mic[k]);
         if (lin_in) {
-            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_far[k], far + off * in_stride, row * (size_t)nb, cudaMemcpyHostToDevice, s));
-            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_mic[k], mic + off * in_stride, row * (size_t)nb, cudaMemcpyHostToDevice, s));
+            ok(cudaMemcpyAsync(up_f, far + off * in_stride, in_row * (size_t)nb, cudaMemcpyHostToDevice, s));
+            ok(cudaMemcpyAsync(up_m, mic + off * in_stride, in_row * (size_t)nb, cudaMemcpyHostToDevice, s));
         } else {
-            AEC_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_far[k], dpitch, far + off * in_stride,
-                                             (size_t)in_stride * sizeof(float), row, (size_t)nb, cudaMemcpyHostToDevice, s));
-            AEC_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_mic[k], dpitch, mic + off * in_stride,
-                                             (size_t)in_stride * sizeof(float), row, (size_t)nb, cudaMemcpyHostToDevice, s));
+            ok(cudaMemcpy2DAsync(up_f, in_dpitch, far + off * in_stride, in_spitch, in_row, (size_t)nb,
+                                 cudaMemcpyHostToDevice, s));
+            ok(cudaMemcpy2DAsync(up_m, in_dpitch, mic + off * in_stride, in_spitch, in_row, (size_t)nb,
+                                 cudaMemcpyHostToDevice, s));
+        }
+        if (!ok(cudaSuccess)) break;
+        if (kPcm) {
+            const long long pairs = (long long)nb * ctx->stride / 2;          // stride is a multiple of 4
+            pcm16_to_f32_kernel<<<sms * 4, 256, 0, s>>>(ctx->d_pcm[k], ctx->d_far[k], pairs);
+            pcm16_to_f32_kernel<<<sms * 4, 256, 0, s>>>(ctx->d_pcm[k] + sig_elems, ctx->d_mic[k], pairs);
+            count_launch(2);
         }
         if (n_samples) {
             memcpy(ctx->h_n[k], n_samples + off, (size_t)nb * sizeof(int64_t));
-            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n[k], ctx->h_n[k], (size_t)nb * sizeof(int64_t),
-                                           cudaMemcpyHostToDevice, s));
+            if (!ok(cudaMemcpyAsync(ctx->d_n[k], ctx->h_n[k], (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s)))
+                break;
         }
         rc = aec_stage1_run(ctx->d_far[k], ctx->d_mic[k], ctx->d_err[k], echo_est ? ctx->d_echo[k] : nullptr,
                             erle_db ? ctx->d_erle[k] : nullptr,
                             n_samples ? reinterpret_cast<const int64_t*>(ctx->d_n[k]) : nullptr, nb, L, ctx->stride,
                             ctx->stride, cfg, s);
-        if (rc != AEC_OK) {
-            first_rc = rc;
-            break;
-        }
-        const bool lin_out = (out_stride == L) && (ctx->stride == L);
+        if (rc != AEC_OK) break;
         if (lin_out) {
-            AEC_CUDA_CHECK(cudaMemcpyAsync(err + off * out_stride, ctx->d_err[k], row * (size_t)nb, cudaMemcpyDeviceToHost, s));
+            ok(cudaMemcpyAsync(err + off * out_stride, ctx->d_err[k], out_row * (size_t)nb, cudaMemcpyDeviceToHost, s));
             if (echo_est)
-                AEC_CUDA_CHECK(cudaMemcpyAsync(echo_est + off * out_stride, ctx->d_echo[k], row * (size_t)nb,
-                                               cudaMemcpyDeviceToHost, s));
+                ok(cudaMemcpyAsync(echo_est + off * out_stride, ctx->d_echo[k], out_row * (size_t)nb,
+                                   cudaMemcpyDeviceToHost, s));
         } else {
-            AEC_CUDA_CHECK(cudaMemcpy2DAsync(err + off * out_stride, (size_t)out_stride * sizeof(float), ctx->d_err[k],
-                                             dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
+            ok(cudaMemcpy2DAsync(err + off * out_stride, out_pitch, ctx->d_err[k], dpitch, out_row, (size_t)nb,
+                                 cudaMemcpyDeviceToHost, s));
             if (echo_est)
-                AEC_CUDA_CHECK(cudaMemcpy2DAsync(echo_est + off * out_stride, (size_t)out_stride * sizeof(float),
-                                                 ctx->d_echo[k], dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
+                ok(cudaMemcpy2DAsync(echo_est + off * out_stride, out_pitch, ctx->d_echo[k], dpitch, out_row, (size_t)nb,
+                                     cudaMemcpyDeviceToHost, s));
         }
         if (erle_db) {
-            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->h_erle[k], ctx->d_erle[k], (size_t)nb * sizeof(float),
-                                           cudaMemcpyDeviceToHost, s));
+            ok(cudaMemcpyAsync(ctx->h_erle[k], ctx->d_erle[k], (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, s));
             ctx->pending_off[k] = off;
             ctx->pending_nb[k] = nb;
         }
     }
-    for (int i = 0; i < kSlots; ++i) {
-        rc = host_ctx_drain(ctx, i, erle_db);
-        if (rc != AEC_OK) return rc;
+    if (e != cudaSuccess) {
+        set_cuda_error(e, "aec_stage1_run_host: copy / launch");
+        rc = AEC_ECUDA;
     }
-    return first_rc;
+    if (rc != AEC_OK) {
+        host_ctx_quiesce(ctx);
+        return rc;
+    }
+    for (int i = 0; i < ctx->slots; ++i) {
+        const int r = host_ctx_drain(ctx, i, erle_db);
+        if (r != AEC_OK && rc == AEC_OK) rc = r;
+    }
+    if (rc != AEC_OK) {
+        host_ctx_quiesce(ctx);
+        return rc;
+    }
+    AEC_CUDA_CHECK(cudaGetLastError());
+    return AEC_OK;
+}
+}  // namespace
+
+extern "C" int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const float* mic, float* err, float* echo_est,
+                                   float* erle_db, const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride,
+                                   int64_t out_stride, const aec_cfg* cfg) {
+    return run_host_impl<float>(ctx, far, mic, err, echo_est, erle_db, n_samples, B, L, in_stride, out_stride, cfg);
 }
 
 extern "C" int aec_stage1_run_host_pcm16(aec_host_ctx* ctx, const int16_t* far, const int16_t* mic, float* err,
                                          float* echo_est, float* erle_db, const int64_t* n_samples, int64_t B,
                                          int64_t L, int64_t in_stride, int64_t out_stride, const aec_cfg* cfg) {
-    if (!ctx) return AEC_EINVAL;
-    int rc = validate_cfg(cfg);
-    if (rc != AEC_OK) return rc;
-    if (B < 0 || L < 0 || L > ctx->max_samples || in_stride < L || out_stride < L) return AEC_EINVAL;
-    if (B == 0) return AEC_OK;
-    if (!far || !mic || !err) return AEC_EINVAL;
-    const size_t pcm_sig = (size_t)ctx->slice * (size_t)ctx->stride;      // int16 elements per signal per slot
-    for (int i = 0; i < kSlots; ++i)
-        if (!ctx->d_pcm[i]) AEC_CUDA_CHECK(cudaMalloc(&ctx->d_pcm[i], 2 * pcm_sig * sizeof(int16_t)));
-    const size_t row = (size_t)L * sizeof(float);
-    const size_t dpitch = (size_t)ctx->stride * sizeof(float);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    int first_rc = AEC_OK;
-    int64_t nb = 0;
-    for (int64_t off = 0, it = 0; off < B; off += nb, ++it) {
-        const int k = (int)(it % kSlots);
-        nb = host_slice(ctx->slice, B - off);
-        cudaStream_t s = ctx->stream[k];
-        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (kSlots slices ago) is done
-        if (rc != AEC_OK) return rc;
-        int16_t* pf = ctx->d_pcm[k];
-        int16_t* pm = ctx->d_pcm[k] + pcm_sig;
-        if (in_stride == L && ctx->stride == L) {
-            AEC_CUDA_CHECK(cudaMemcpyAsync(pf, far + off * in_stride, (size_t)L * 2 * (size_t)nb, cudaMemcpyHostToDevice, s));
-            AEC_CUDA_CHECK(cudaMemcpyAsync(pm, mic + off * in_stride, (size_t)L * 2 * (size_t)nb, cudaMemcpyHostToDevice, s));
-        } else {
-            AEC_CUDA_CHECK(cudaMemcpy2DAsync(pf, (size_t)ctx->stride * 2, far + off * in_stride, (size_t)in_stride * 2,
-                                             (size_t)L * 2, (size_t)nb, cudaMemcpyHostToDevice, s));
-            AEC_CUDA_CHECK(cudaMemcpy2DAsync(pm, (size_t)ctx->stride * 2, mic + off * in_stride, (size_t)in_stride * 2,
-                                             (size_t)L * 2, (size_t)nb, cudaMemcpyHostToDevice, s));
-        }
-        const long long pairs = (long long)nb * ctx->stride / 2;          // stride is a multiple of 4
-        pcm16_to_f32_kernel<<<sms * 4, 256, 0, s>>>(pf, ctx->d_far[k], pairs);
-        pcm16_to_f32_kernel<<<sms * 4, 256, 0, s>>>(pm, ctx->d_mic[k], pairs);
-        count_launch(2);
-        if (n_samples) {
-            memcpy(ctx->h_n[k], n_samples + off, (size_t)nb * sizeof(int64_t));
-            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n[k], ctx->h_n[k], (size_t)nb * sizeof(int64_t),
-                                           cudaMemcpyHostToDevice, s));
-        }
-        rc = aec_stage1_run(ctx->d_far[k], ctx->d_mic[k], ctx->d_err[k], echo_est ? ctx->d_echo[k] : nullptr,
-                            erle_db ? ctx->d_erle[k] : nullptr,
-                            n_samples ? reinterpret_cast<const int64_t*>(ctx->d_n[k]) : nullptr, nb, L, ctx->stride,
-                            ctx->stride, cfg, s);
-        if (rc != AEC_OK) {
-            first_rc = rc;
-            break;
-        }
-        if (out_stride == L && ctx->stride == L) {
-            AEC_CUDA_CHECK(cudaMemcpyAsync(err + off * out_stride, ctx->d_err[k], row * (size_t)nb, cudaMemcpyDeviceToHost, s));
-            if (echo_est)
-                AEC_CUDA_CHECK(cudaMemcpyAsync(echo_est + off * out_stride, ctx->d_echo[k], row * (size_t)nb,
-                                               cudaMemcpyDeviceToHost, s));
-        } else {
-            AEC_CUDA_CHECK(cudaMemcpy2DAsync(err + off * out_stride, (size_t)out_stride * sizeof(float), ctx->d_err[k],
-                                             dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
-            if (echo_est)
-                AEC_CUDA_CHECK(cudaMemcpy2DAsync(echo_est + off * out_stride, (size_t)out_stride * sizeof(float),
-                                                 ctx->d_echo[k], dpitch, row, (size_t)nb, cudaMemcpyDeviceToHost, s));
-        }
-        if (erle_db) {
-            AEC_CUDA_CHECK(cudaMemcpyAsync(ctx->h_erle[k], ctx->d_erle[k], (size_t)nb * sizeof(float),
-                                           cudaMemcpyDeviceToHost, s));
-            ctx->pending_off[k] = off;
-            ctx->pending_nb[k] = nb;
-        }
-    }
-    for (int i = 0; i < kSlots; ++i) {
-        rc = host_ctx_drain(ctx, i, erle_db);
-        if (rc != AEC_OK) return rc;
-    }
-    AEC_CUDA_CHECK(cudaGetLastError());
-    return first_rc;
+    return run_host_impl<int16_t>(ctx, far, mic, err, echo_est, erle_db, n_samples, B, L, in_stride, out_stride, cfg);
 }
 
-extern "C" int aec_host_alloc(void** ptr, int64_t bytes) {
+extern "C" int aec_host_alloc_ex(void** ptr, int64_t bytes, int32_t flags) {
     if (!ptr || bytes <= 0) return AEC_EINVAL;
-    AEC_CUDA_CHECK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    unsigned f = cudaHostAllocDefault;
+    if (flags & AEC_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+    if (flags & AEC_HOST_PORTABLE) f |= cudaHostAllocPortable;
+    AEC_CUDA_CHECK(cudaHostAlloc(ptr, (size_t)bytes, f));
     return AEC_OK;
 }
+
+extern "C" int aec_host_alloc(void** ptr, int64_t bytes) { return aec_host_alloc_ex(ptr, bytes, 0); }
 
 extern "C" int aec_host_free(void* ptr) {
     if (!ptr) return AEC_OK;
     AEC_CUDA_CHECK(cudaFreeHost(ptr));
     return AEC_OK;
+}
+
+extern "C" int aec_host_is_pinned(const void* ptr) {
+    if (!ptr) return AEC_EINVAL;
+    cudaPointerAttributes a{};
+    const cudaError_t e = cudaPointerGetAttributes(&a, ptr);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ cudaError_t launch_stage1_1024(int P, int algo, bool echo, int regs, const Stage
     AEC_TRY_1024(1, kAlgoNlms, true, 128)
     AEC_TRY_1024(1, kAlgoKalman, false, 128)
     AEC_TRY_1024(1, kAlgoKalman, true, 128)
-    return cudaErrorInvalidValue;
+    return kNoInstance;
 }
 
 }  // namespace aec

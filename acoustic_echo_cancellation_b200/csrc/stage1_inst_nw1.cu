@@ -7,7 +7,7 @@ namespace aec {
 cudaError_t launch_stage1_nw1(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s) {
     AEC_TRY_INSTANCE(1, 4, kAlgoNlms, false, 255)
     AEC_TRY_INSTANCE(1, 4, kAlgoNlms, false, 200)
-    return cudaErrorInvalidValue;
+    return kNoInstance;
 }
 
 }  // namespace aec

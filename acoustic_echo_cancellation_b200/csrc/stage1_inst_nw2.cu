@@ -21,7 +21,7 @@ cudaError_t launch_stage1_nw2(int P, int algo, bool echo, int regs, const Stage1
     AEC_TRY_INSTANCE(2, 2, kAlgoNlms, true, 128)
     AEC_TRY_INSTANCE(2, 2, kAlgoKalman, false, 128)
     AEC_TRY_INSTANCE(2, 2, kAlgoKalman, true, 128)
-    return cudaErrorInvalidValue;
+    return kNoInstance;
 }
 
 }  // namespace aec

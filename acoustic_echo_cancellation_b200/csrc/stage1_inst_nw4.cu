@@ -15,7 +15,7 @@ cudaError_t launch_stage1_nw4(int P, int algo, bool echo, int regs, const Stage1
     AEC_TRY_INSTANCE(4, 16, kAlgoKalman, true, 255)
     AEC_TRY_INSTANCE(4, 4, kAlgoNlms, false, 128)
     AEC_TRY_INSTANCE(4, 4, kAlgoNlms, false, 96)
-    return cudaErrorInvalidValue;
+    return kNoInstance;
 }
 
 }  // namespace aec

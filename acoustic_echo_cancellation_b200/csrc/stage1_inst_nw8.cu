@@ -13,7 +13,7 @@ cudaError_t launch_stage1_nw8(int P, int algo, bool echo, int regs, const Stage1
     AEC_TRY_INSTANCE(8, 8, kAlgoKalman, true, 128)
     AEC_TRY_INSTANCE(8, 8, kAlgoNlms, false, 128)
     AEC_TRY_INSTANCE(8, 8, kAlgoNlms, true, 128)
-    return cudaErrorInvalidValue;
+    return kNoInstance;
 }
 
 }  // namespace aec

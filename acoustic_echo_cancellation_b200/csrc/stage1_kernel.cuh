@@ -37,6 +37,9 @@ namespace aec {
 
 enum { kAlgoNlms = 0, kAlgoKalman = 1 };
 
+// "this (P, algo, echo, register cap) is not instantiated": a code no launch path of the runtime produces
+constexpr cudaError_t kNoInstance = cudaErrorStubLibrary;
+
 struct Stage1Params {
     const float* far;
     const float* mic;

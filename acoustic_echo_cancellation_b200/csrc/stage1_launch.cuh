@@ -8,8 +8,10 @@
 
 namespace aec {
 
-// Returns cudaSuccess after launching, cudaErrorInvalidValue when (P, algo, echo, regs) is not
-// instantiated in that unit ("not built" -> AEC_EUNSUPPORTED at the ABI).
+// Returns cudaSuccess after launching, kNoInstance when (P, algo, echo, regs) is not instantiated in that
+// unit ("not built" -> AEC_EUNSUPPORTED at the ABI) -- a code no launch path of the runtime produces, so that
+// genuine cudaErrorInvalidValue failures (attributes, occupancy query, launch) surface as AEC_ECUDA
+// (kNoInstance is declared in stage1_kernel.cuh).
 cudaError_t launch_stage1_nw1(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
 cudaError_t launch_stage1_nw2(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
 cudaError_t launch_stage1_nw4(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);

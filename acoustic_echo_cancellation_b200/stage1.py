@@ -135,14 +135,19 @@ class HostPipeline:
     in slices.  This is the call a ``create_h5``-style data-prep
     loop makes (Stage2_lhm/generate_h5files/train_wav2h5.py:20-42)."""
 
-    def __init__(self, slice_utterances: int, max_samples: int, device: int = 0):
+    def __init__(self, slice_utterances: int, max_samples: int, device: int = 0, slots: int = 0,
+                 ramp: bool = True):
+        """``slots``: slices in flight (0 = library default, 4); ``ramp``: grow the first slices from 16
+        utterances so that the first download starts early.  One context per thread: a pipeline is not
+        re-entrant (include/aec_b200.h)."""
         self.device = device
         self._ctx = C.c_void_p()
         self._lib = _lib.load()
         with torch.cuda.device(device):
-            _lib.check(self._lib.aec_host_ctx_create(C.byref(self._ctx), int(slice_utterances), int(max_samples)),
-                       "aec_host_ctx_create")
+            _lib.check(self._lib.aec_host_ctx_create_ex(C.byref(self._ctx), int(slice_utterances), int(max_samples),
+                                                        int(slots), 0 if ramp else 1), "aec_host_ctx_create_ex")
         self.max_samples = int(max_samples)
+        self.slice_utterances = int(slice_utterances)
 
     def close(self):
         if self._ctx:
@@ -190,10 +195,43 @@ class HostPipeline:
         return err
 
 
-def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
-    """numpy array in page-locked host memory (via torch's pinned allocator)."""
-    t = torch.empty(tuple(shape), dtype=torch.from_numpy(np.empty(0, dtype=dtype)).dtype, pin_memory=True)
-    return t.numpy()
+class _PinnedBlock:
+    """Owner of one ``aec_host_alloc_ex`` allocation; freed when the last numpy view of it dies."""
+
+    def __init__(self, nbytes: int, flags: int):
+        self.ptr = C.c_void_p()
+        self._lib = _lib.load()
+        _lib.check(self._lib.aec_host_alloc_ex(C.byref(self.ptr), int(nbytes), int(flags)), "aec_host_alloc_ex")
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.aec_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+HOST_WRITE_COMBINED = 1
+HOST_PORTABLE = 2
+
+
+def pinned_empty(shape, dtype=np.float32, flags: int = 0) -> np.ndarray:
+    """numpy array in page-locked host memory (``aec_host_alloc_ex``: cudaHostAlloc).  ``flags``:
+    ``HOST_WRITE_COMBINED`` for buffers the CPU only writes (inputs), ``HOST_PORTABLE``."""
+    shape = tuple(int(x) for x in shape)
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if shape else 1
+    block = _PinnedBlock(max(n * dt.itemsize, 1), flags)
+    buf = (C.c_char * block.nbytes).from_address(block.ptr.value)
+    buf._aec_owner = block            # keeps the allocation alive as long as any view of `buf` is
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+
+def is_pinned(a: np.ndarray) -> bool:
+    """True if the array's memory is page-locked host memory known to CUDA (``aec_host_is_pinned``)."""
+    return int(_lib.load().aec_host_is_pinned(a.ctypes.data)) == 1
 
 
 def fp32_peak_tflops(iters: int = 4096) -> float:

@@ -1,29 +1,47 @@
 """Drop-in for the reference's wav -> h5 generators with the stage-1 canceller inserted.
 
+    create_h5(args)        <-> ``create_h5(args)`` of all three scripts (dispatches on the arguments like the
+                               scripts' own ``main()`` do)
     create_h5_train(args)  <-> Stage2_lhm/generate_h5files/train_wav2h5.py:10-52
     create_h5_test(args)   <-> Stage2_lhm/generate_h5files/test_wav2h5.py:10-64
+    create_h5_val(args)    <-> Stage2_lhm/generate_h5files/val_wav2h5.py:10-59
 
-Same argparse flags (``--train_path``/``--val_path``, ``--h5_path``, ``--list_path``, ``--sr``), same
-file names (``tr/tr_<idx>.ex``, ``tt/test.ex``, ``tr_list.txt``, ``tt_list.txt``, ``filename.txt``) and the
-same four dataset keys, so the reference readers (Stage2_lhm/scripts/train1.py:33-40,
-scripts/test.py:20-33) keep working; two datasets are ADDED beside them: ``stage1_error`` and
-``stage1_echo``.  In ``test.ex`` they go INSIDE each numbered group because ``ValidateDataset`` counts
-root members (scripts/test.py:23).
+Same argparse flags (``--train_path``/``--val_path``, ``--h5_path``, ``--list_path``, ``--sr``), same file
+names (``tr/tr_<idx>.ex``, ``tt/test.ex``, ``tt/test2.ex``, ``tr_list.txt``, ``tt_list.txt``, ``tt_list2.txt``,
+``filename.txt``) and the same dataset keys (``nearend_speech``/``nearend_mic``/``farend_speech``/``echo``;
+``mic``/``ref``/``near``/``echo`` for the val form), so the reference readers (Stage2_lhm/scripts/train1.py:33-40,
+scripts/test.py:20-33, scripts/utils/data_utils.py:31-34) keep working; two datasets are ADDED beside them:
+``stage1_error`` and ``stage1_echo``.  In ``test.ex`` / ``test2.ex`` they go INSIDE each numbered group because
+``ValidateDataset`` counts root members (scripts/test.py:23).
 
-Utterances are batched through the fused CUDA kernel (host-buffer C ABI); with ``torch.distributed``
-initialised each rank converts a contiguous shard of the file list and rank 0 writes the merged lists.
-``h5py`` is required to write (it is absent from the build image; the import is deferred so the
-module can be imported and its batching logic tested without it).  wav decoding uses ``librosa`` when
-present (as the reference does), else ``scipy.io.wavfile`` + polyphase resampling.
+How a run is organised (the reference is one serial loop: decode 4 wavs, write, next utterance):
+
+    decode batch k+1  (thread pool, 16-bit PCM read straight into page-locked int16 batch buffers: ingest.py)
+    stage 1 on batch k (``aec_stage1_run_host[_pcm16]``: H2D / kernel / D2H pipelined in slices; one C call,
+                        GIL released)
+    write batch k-1    (thread pool; one file per utterance for the train form, one ordered writer for test / val)
+
+all three overlapped, three buffer sets cycling.  With ``torch.distributed`` initialised each rank converts a
+contiguous shard of the SORTED id list on its own GPU (LOCAL_RANK) and rank 0 writes the merged list.
+
+``h5py`` is required to write the reference's ``.ex`` (HDF5) files.  It is absent from the build image, so the
+import is deferred, and ``NpzStore`` -- same ``File / create_group / create_dataset / close`` surface, one
+uncompressed ``.npz`` per file with ``group/key`` member names -- can stand in (``h5=NpzStore()``) where the
+pipeline is to be run and timed without it; the files it writes are NOT readable by the reference's readers.
 """
 from __future__ import annotations
 
 import argparse
 import glob
 import os
-from typing import Callable, Dict, List, Optional
+import time
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
+
+from . import ingest
+from .ingest import load_wav  # noqa: F401  (re-exported: the reference-shaped single-file loader)
 
 KEYS = ("nearend_speech", "nearend_mic", "farend_speech", "echo")
 WAV_PATTERNS = {
@@ -32,38 +50,14 @@ WAV_PATTERNS = {
     "farend_speech": "farend_speech_fileid_{idx}.wav",
     "echo": "echo_fileid_{idx}.wav",
 }
+# val_wav2h5.py:11-14,33-36,43-46: sub-directory per signal, older key names
+VAL_KEYS = {"mic": "nearend_mic", "ref": "farend_speech", "near": "nearend_speech", "echo": "echo"}
 
 
-def load_wav(path: str, sr: int) -> np.ndarray:
-    """mono float32 at ``sr`` (what ``librosa.load(path, sr=sr)`` returns, train_wav2h5.py:20)."""
-    try:
-        import librosa  # type: ignore
-
-        y, _ = librosa.load(path, sr=sr)
-        return y.astype(np.float32)
-    except ImportError:
-        pass
-    from scipy.io import wavfile
-    from scipy.signal import resample_poly
-
-    rate, data = wavfile.read(path)
-    if data.dtype.kind == "i":
-        data = data.astype(np.float32) / float(2 ** (8 * data.dtype.itemsize - 1))
-    elif data.dtype.kind == "u":
-        data = (data.astype(np.float32) - 128.0) / 128.0
-    data = data.astype(np.float32)
-    if data.ndim == 2:
-        data = data.mean(axis=1)
-    if rate != sr:
-        g = np.gcd(int(rate), int(sr))
-        data = resample_poly(data, sr // g, rate // g).astype(np.float32)
-    return data
-
-
-def list_utterance_ids(folder: str) -> List[str]:
+def list_utterance_ids(folder: str, pattern: str = "nearend_speech_fileid_*.wav") -> List[str]:
     """ids in the order ``glob`` yields them (train_wav2h5.py:13-17)."""
     ids = []
-    for p in glob.glob(os.path.join(folder, "nearend_speech_fileid_*.wav")):
+    for p in glob.glob(os.path.join(folder, pattern)):
         ids.append(os.path.basename(p).split(".wav")[0].split("_")[-1])
     return ids
 
@@ -99,67 +93,272 @@ def _stage1_batch(far: List[np.ndarray], mic: List[np.ndarray], runner: Callable
     return [err[i, :n[i]] for i in range(len(far))], [echo[i, :n[i]] for i in range(len(far))]
 
 
-def default_runner(cfg=None, slice_utterances: int = 256, device: int = 0) -> Callable:
-    """Runner backed by ``aec_stage1_run_host`` (no CPU fallback)."""
-    from .stage1 import HostPipeline, Stage1Config
+def _local_device() -> int:
+    """CUDA device of this rank: LOCAL_RANK under torchrun, else the current device."""
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    try:
+        import torch
 
-    cfg = cfg or Stage1Config()
-    state: Dict[str, object] = {}
+        return int(torch.cuda.current_device()) if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
 
-    def run(far: np.ndarray, mic: np.ndarray, n: np.ndarray):
-        pipe = state.get("pipe")
-        if pipe is None or pipe.max_samples < far.shape[1]:
-            pipe = HostPipeline(slice_utterances, far.shape[1], device)
-            state["pipe"] = pipe
-        err = np.empty(far.shape, dtype=np.float32)          # (inputs may be int16 PCM; outputs are float32)
-        echo = np.empty(far.shape, dtype=np.float32)
-        pipe.run(far, mic, cfg, n_samples=n, err=err, echo=echo)
+
+class Stage1Runner:
+    """``runner(far, mic, n) -> (err, echo)`` backed by ``aec_stage1_run_host`` / ``_pcm16`` (no CPU fallback).
+
+    Inputs that are not page-locked (arrays a caller got from ``librosa.load`` and stacked with numpy) are staged
+    through page-locked buffers first: a ``cudaMemcpyAsync`` from pageable memory is staged by the driver and
+    serialises the slices of the pipeline.  Outputs are page-locked buffers owned by the runner, valid until the
+    call after next (two sets alternate), which is what lets a writer thread drain batch k while batch k+1 runs."""
+
+    def __init__(self, cfg=None, slice_utterances: int = 128, device: Optional[int] = None, want_echo: bool = True):
+        from .stage1 import Stage1Config
+
+        self.cfg = cfg or Stage1Config()
+        self.slice_utterances = int(slice_utterances)
+        self.device = _local_device() if device is None else int(device)
+        self.want_echo = want_echo
+        self.pipe = None
+        self._in: Dict[str, np.ndarray] = {}
+        self._out: List[Dict[str, np.ndarray]] = [{}, {}]
+        self._flip = 0
+        self.seconds = 0.0          # time spent inside the C call (for the pipeline report)
+
+    def _pinned(self, store: dict, key: str, shape, dtype) -> np.ndarray:
+        from .stage1 import pinned_empty
+
+        buf = store.get(key)
+        if buf is None or buf.dtype != np.dtype(dtype) or buf.shape[0] < shape[0] or buf.shape[1] < shape[1]:
+            rows = max(shape[0], buf.shape[0] if buf is not None and buf.dtype == np.dtype(dtype) else 0)
+            cols = max(shape[1], buf.shape[1] if buf is not None and buf.dtype == np.dtype(dtype) else 0)
+            import torch
+
+            with torch.cuda.device(self.device):
+                buf = pinned_empty((rows, cols), dtype)
+            store[key] = buf
+        return buf[:shape[0], :shape[1]]
+
+    def __call__(self, far: np.ndarray, mic: np.ndarray, n: np.ndarray):
+        from .stage1 import HostPipeline, is_pinned
+
+        if self.pipe is None or self.pipe.max_samples < far.shape[1]:
+            if self.pipe is not None:
+                self.pipe.close()
+            self.pipe = HostPipeline(self.slice_utterances, far.shape[1], self.device)
+        if not (is_pinned(far) and is_pinned(mic)):
+            sf = self._pinned(self._in, "far", far.shape, far.dtype)
+            sm = self._pinned(self._in, "mic", mic.shape, mic.dtype)
+            np.copyto(sf, far)
+            np.copyto(sm, mic)
+            far, mic = sf, sm
+        out = self._out[self._flip]
+        self._flip ^= 1
+        err = self._pinned(out, "err", far.shape, np.float32)
+        echo = self._pinned(out, "echo", far.shape, np.float32) if self.want_echo else None
+        t0 = time.perf_counter()
+        self.pipe.run(far, mic, self.cfg, n_samples=n, err=err, echo=echo)
+        self.seconds += time.perf_counter() - t0
         return err, echo
 
-    return run
+    def buffers_pinned(self) -> bool:
+        """True when every staging / output buffer this runner has allocated is page-locked (tested on the GPU)."""
+        from .stage1 import is_pinned
+
+        bufs = list(self._in.values()) + [b for o in self._out for b in o.values()]
+        return bool(bufs) and all(is_pinned(b) for b in bufs)
+
+    def close(self):
+        if self.pipe is not None:
+            self.pipe.close()
+            self.pipe = None
+
+
+def default_runner(cfg=None, slice_utterances: int = 128, device: Optional[int] = None) -> Callable:
+    """Runner backed by ``aec_stage1_run_host`` on this rank's GPU (LOCAL_RANK under torchrun)."""
+    return Stage1Runner(cfg, slice_utterances, device)
 
 
 def _h5py():
     try:
         import h5py  # type: ignore
     except ImportError as e:  # pragma: no cover - depends on the box
-        raise ImportError("writing the reference's .ex (HDF5) files needs h5py, which is not installed") from e
+        raise ImportError("writing the reference's .ex (HDF5) files needs h5py, which is not installed "
+                          "(pass h5=NpzStore() to run the pipeline with the stand-in container)") from e
     return h5py
 
 
-def _shard(ids: List[str]):
-    import torch.distributed as dist
+class _NpzGroup:
+    def __init__(self, root: "_NpzFile", prefix: str):
+        self._root, self._prefix = root, prefix
 
+    def create_dataset(self, name, data=None, shape=None, chunks=None):
+        self._root._members[self._prefix + name] = np.ascontiguousarray(data)
+
+    def create_group(self, name):
+        return _NpzGroup(self._root, self._prefix + str(name) + "/")
+
+
+class _NpzFile(_NpzGroup):
+    def __init__(self, path: str):
+        super().__init__(self, "")
+        self._path, self._members = path, {}
+
+    def close(self):
+        with open(self._path, "wb") as f:          # exact file name (np.savez would append ".npz" to a str path)
+            np.savez(f, **self._members)
+        self._members = {}
+
+
+class NpzStore:
+    """Stand-in container with the slice of the ``h5py`` surface the generators use, for boxes without h5py:
+    one uncompressed npz (zip of .npy) per ``File``, member names ``<group>/<dataset>``."""
+
+    def File(self, name, mode):
+        assert mode == "w"
+        return _NpzFile(name)
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except Exception:
+        pass
+    return None
+
+
+def _shard(ids: List[str]):
+    """This rank's contiguous shard of the SORTED id list (glob order is filesystem-dependent: ranks on different
+    nodes could otherwise see different orders and drop / duplicate utterances).  A single process keeps the glob
+    order, like the reference."""
     from .sharding import shard_range
 
-    if dist.is_available() and dist.is_initialized():
-        lo, hi = shard_range(len(ids), dist.get_rank(), dist.get_world_size())
-        return ids[lo:hi], dist.get_rank()
+    dist = _dist()
+    if dist is not None and dist.get_world_size() > 1:
+        ordered = sorted(ids, key=lambda s: (len(s), s))
+        lo, hi = shard_range(len(ordered), dist.get_rank(), dist.get_world_size())
+        return ordered[lo:hi], dist.get_rank()
     return ids, 0
 
 
-def create_h5_train(args, runner: Optional[Callable] = None, batch: int = 256, h5=None):
+def _create_dataset(g, name: str, a: np.ndarray, shape=None):
+    """``create_dataset(name, data=a.astype(float32), shape=a.shape, chunks=True)`` as the reference writes it;
+    h5py rejects ``chunks=True`` for an empty dataset (an utterance shorter than one hop has an empty stage-1
+    output), so those are written contiguous."""
+    a = ingest.as_float32(a)
+    shape = a.shape if shape is None else shape
+    if a.size == 0 or int(np.prod(shape)) == 0:
+        g.create_dataset(name, data=a, shape=shape)
+    else:
+        g.create_dataset(name, data=a, shape=shape, chunks=True)
+
+
+class _Engine:
+    """decode | stage 1 | write, overlapped.  ``emit(k, ids, batch, errs, echos)`` writes one finished batch."""
+
+    def __init__(self, sr: int, runner: Optional[Callable], batch: int, decode_threads: int, pinned: bool):
+        alloc = None
+        if pinned:
+            from .stage1 import pinned_empty
+
+            alloc = lambda shape, dtype: pinned_empty(shape, dtype)      # noqa: E731
+        self.runner = runner or default_runner()
+        self.decoder = ingest.BatchDecoder(sr, threads=decode_threads, alloc=alloc, sets=3)
+        self.batch = int(batch)
+        self.stats = {"decode_s": 0.0, "stage1_s": 0.0, "write_s": 0.0, "wall_s": 0.0, "utterances": 0,
+                      "pcm16_batches": 0, "float32_batches": 0}
+
+    def _decode(self, paths):
+        t0 = time.perf_counter()
+        b = self.decoder.decode(paths["far"], paths["mic"], paths["extra"])
+        self.stats["decode_s"] += time.perf_counter() - t0
+        return b
+
+    def _run(self, b: ingest.DecodedBatch):
+        t0 = time.perf_counter()
+        err, echo = self.runner(b.far, b.mic, b.n)
+        self.stats["stage1_s"] += time.perf_counter() - t0
+        self.stats["pcm16_batches" if b.pcm16 else "float32_batches"] += 1
+        nb = len(b.n)
+        return [err[i, :b.n[i]] for i in range(nb)], [echo[i, :b.n[i]] for i in range(nb)]
+
+    def run(self, ids: Sequence[str], paths_of: Callable[[Sequence[str]], dict], emit: Callable):
+        t_start = time.perf_counter()
+        chunks = [list(ids[i:i + self.batch]) for i in range(0, len(ids), self.batch)]
+        with ThreadPoolExecutor(1, thread_name_prefix="aec-decode") as dec, \
+                ThreadPoolExecutor(1, thread_name_prefix="aec-gpu") as gpu, \
+                ThreadPoolExecutor(1, thread_name_prefix="aec-write") as wr:
+
+            def timed_emit(*a):
+                t0 = time.perf_counter()
+                emit(*a)
+                self.stats["write_s"] += time.perf_counter() - t0
+
+            writes = []
+            fut_dec = dec.submit(self._decode, paths_of(chunks[0])) if chunks else None
+            for k, chunk in enumerate(chunks):
+                b = fut_dec.result()
+                # batch k-2 must be on disk before its buffers are reused: the decoder cycles three buffer sets
+                # (batch k+1 decodes into the set of batch k-2) and the runner's output sets alternate (batch k
+                # writes where batch k-2 did)
+                if k >= 2:
+                    writes[k - 2].result()
+                if k + 1 < len(chunks):
+                    fut_dec = dec.submit(self._decode, paths_of(chunks[k + 1]))
+                errs, echos = gpu.submit(self._run, b).result()
+                writes.append(wr.submit(timed_emit, k, chunk, b, errs, echos))
+                self.stats["utterances"] += len(chunk)
+            for w in writes:
+                w.result()
+        self.decoder.close()
+        self.stats["wall_s"] = time.perf_counter() - t_start
+        return self.stats
+
+
+def _train_paths(folder: str):
+    def paths_of(chunk):
+        p = lambda k: [os.path.join(folder, WAV_PATTERNS[k].format(idx=i)) for i in chunk]      # noqa: E731
+        return {"far": p("farend_speech"), "mic": p("nearend_mic"),
+                "extra": {"nearend_speech": p("nearend_speech"), "echo": p("echo")}}
+    return paths_of
+
+
+def _signal(b: ingest.DecodedBatch, key: str, j: int) -> np.ndarray:
+    return b.signals[{"farend_speech": "__far__", "nearend_mic": "__mic__"}.get(key, key)][j]
+
+
+def create_h5_train(args, runner: Optional[Callable] = None, batch: int = 256, h5=None, decode_threads: int = 8,
+                    write_threads: int = 8, pinned: Optional[bool] = None, stats: Optional[dict] = None):
     """``create_h5(args)`` of train_wav2h5.py with stage 1 inserted.  One ``tr_<idx>.ex`` per utterance."""
     h5 = h5 or _h5py()
-    runner = runner or default_runner()
     ids, rank = _shard(list_utterance_ids(args.train_path))
     os.makedirs(os.path.join(args.h5_path, "tr"), exist_ok=True)
-    train_list: List[str] = []
-    for b0 in range(0, len(ids), batch):
-        chunk = ids[b0:b0 + batch]
-        sig = {k: [load_wav(os.path.join(args.train_path, WAV_PATTERNS[k].format(idx=i)), args.sr) for i in chunk]
-               for k in KEYS}
-        errs, echos = _stage1_batch(sig["farend_speech"], sig["nearend_mic"], runner)
-        for j, idx in enumerate(chunk):
-            name = os.path.join(args.h5_path, "tr", "tr_" + idx + ".ex")
-            train_list.append(str(name))
-            w = h5.File(name, "w")
-            for k in KEYS:                                                   # train_wav2h5.py:39-42
-                a = sig[k][j].astype(np.float32)
-                w.create_dataset(k, data=a, shape=a.shape, chunks=True)
-            w.create_dataset("stage1_error", data=errs[j], shape=errs[j].shape, chunks=True)
-            w.create_dataset("stage1_echo", data=echos[j], shape=echos[j].shape, chunks=True)
-            w.close()
+    train_list = [str(os.path.join(args.h5_path, "tr", "tr_" + idx + ".ex")) for idx in ids]
+    eng = _Engine(args.sr, runner, batch, decode_threads, pinned=(runner is None) if pinned is None else pinned)
+    pool = ThreadPoolExecutor(max(1, write_threads), thread_name_prefix="aec-h5")
+
+    def write_one(name, b, j, err, echo):
+        w = h5.File(name, "w")
+        for k in KEYS:                                                   # train_wav2h5.py:39-42
+            _create_dataset(w, k, _signal(b, k, j))
+        _create_dataset(w, "stage1_error", err)
+        _create_dataset(w, "stage1_echo", echo)
+        w.close()
+
+    def emit(k, chunk, b, errs, echos):
+        futs = [pool.submit(write_one, os.path.join(args.h5_path, "tr", "tr_" + idx + ".ex"), b, j, errs[j], echos[j])
+                for j, idx in enumerate(chunk)]
+        for f in futs:
+            f.result()
+
+    st = eng.run(ids, _train_paths(args.train_path), emit)
+    pool.shutdown()
+    if stats is not None:
+        stats.update(st)
     from .sharding import merge_filelists
 
     merged = merge_filelists(train_list)
@@ -169,46 +368,102 @@ def create_h5_train(args, runner: Optional[Callable] = None, batch: int = 256, h
     return merged
 
 
-def create_h5_test(args, runner: Optional[Callable] = None, batch: int = 256, h5=None, filename: str = "test.ex"):
-    """``create_h5(args)`` of test_wav2h5.py with stage 1 inserted.  One file, one numbered group per
-    utterance; single writer (rank 0 semantics: call it on one rank)."""
+def _single_file(args, ids, paths_of, keymap, h5, runner, batch, filename, list_name, names, decode_threads, pinned,
+                 stats, echo_shape_of_near: bool):
+    """Shared body of the test / val forms: ONE file, one numbered group per utterance, written in order by one
+    writer (call it on one rank)."""
     h5 = h5 or _h5py()
-    runner = runner or default_runner()
-    ids = list_utterance_ids(args.val_path)
     os.makedirs(os.path.join(args.h5_path, "tt"), exist_ok=True)
     path = os.path.join(args.h5_path, "tt", filename)
     w = h5.File(path, "w")
-    count = 0
-    for b0 in range(0, len(ids), batch):
-        chunk = ids[b0:b0 + batch]
-        sig = {k: [load_wav(os.path.join(args.val_path, WAV_PATTERNS[k].format(idx=i)), args.sr) for i in chunk]
-               for k in KEYS}
-        errs, echos = _stage1_batch(sig["farend_speech"], sig["nearend_mic"], runner)
+    count = [0]
+    eng = _Engine(args.sr, runner, batch, decode_threads, pinned=(runner is None) if pinned is None else pinned)
+
+    def emit(k, chunk, b, errs, echos):
         for j in range(len(chunk)):
-            g = w.create_group(str(count))                                   # test_wav2h5.py:44
-            for k in KEYS:                                                   # test_wav2h5.py:45-48
-                a = sig[k][j].astype(np.float32)
-                g.create_dataset(k, data=a, shape=a.shape, chunks=True)
-            g.create_dataset("stage1_error", data=errs[j], shape=errs[j].shape, chunks=True)
-            g.create_dataset("stage1_echo", data=echos[j], shape=echos[j].shape, chunks=True)
-            count += 1
+            g = w.create_group(str(count[0]))                                # test_wav2h5.py:44, val_wav2h5.py:42
+            for out_key, src_key in keymap.items():
+                a = _signal(b, src_key, j)
+                shape = None
+                if echo_shape_of_near and out_key == "echo":                 # val_wav2h5.py:46: shape=near.shape
+                    shape = _signal(b, "nearend_speech", j).shape
+                    a = ingest.as_float32(a)
+                    if a.shape != shape:                                     # h5py would broadcast-or-raise; keep the data
+                        shape = a.shape
+                _create_dataset(g, out_key, a, shape)
+            _create_dataset(g, "stage1_error", errs[j])
+            _create_dataset(g, "stage1_echo", echos[j])
+            count[0] += 1
+
+    st = eng.run(ids, paths_of, emit)
     w.close()
-    with open(os.path.join(args.list_path, "tt_list.txt"), "w") as f:         # test_wav2h5.py:55-58
+    if stats is not None:
+        stats.update(st)
+    with open(os.path.join(args.list_path, list_name), "w") as f:             # test_wav2h5.py:55-58
         f.write(str(path))
     with open(os.path.join(args.list_path, "filename.txt"), "w") as f:        # test_wav2h5.py:60-62
-        f.write("\n".join(ids))
+        f.write("\n".join(names))
     return path
 
 
+def create_h5_test(args, runner: Optional[Callable] = None, batch: int = 256, h5=None, filename: str = "test.ex",
+                   decode_threads: int = 8, pinned: Optional[bool] = None, stats: Optional[dict] = None):
+    """``create_h5(args)`` of test_wav2h5.py with stage 1 inserted: ``tt/test.ex``, groups "0", "1", ... with the
+    four reference datasets + the two stage-1 ones; ``tt_list.txt``; ``filename.txt`` holds the ids."""
+    ids = list_utterance_ids(args.val_path)
+    return _single_file(args, ids, _train_paths(args.val_path), {k: k for k in KEYS}, h5, runner, batch, filename,
+                        "tt_list.txt", ids, decode_threads, pinned, stats, echo_shape_of_near=False)
+
+
+def create_h5_val(args, runner: Optional[Callable] = None, batch: int = 256, h5=None, filename: str = "test2.ex",
+                  decode_threads: int = 8, pinned: Optional[bool] = None, stats: Optional[dict] = None):
+    """``create_h5(args)`` of val_wav2h5.py with stage 1 inserted: one sub-directory per signal under
+    ``--val_path`` (``farend_speech/``, ``nearend_speech/``, ``nearend_mic/``, ``echo/``), utterances enumerated
+    from ``nearend_mic/*.wav`` (val_wav2h5.py:24), keys ``mic`` / ``ref`` / ``near`` / ``echo`` (:43-46),
+    ``tt/test2.ex``, ``tt_list2.txt``; ``filename.txt`` holds the microphone BASENAMES (:28)."""
+    mic_dir = os.path.join(args.val_path, "nearend_mic")
+    names, ids = [], []
+    for p in glob.glob(os.path.join(mic_dir, "*.wav")):
+        base = os.path.basename(p)
+        names.append(base)
+        ids.append(base.split("_")[-1].split(".wav")[0])                      # val_wav2h5.py:27-30
+    name_of = dict(zip(ids, names))
+
+    def paths_of(chunk):
+        sub = lambda d, k: [os.path.join(args.val_path, d, WAV_PATTERNS[k].format(idx=i)) for i in chunk]   # noqa: E731
+        return {"far": sub("farend_speech", "farend_speech"),
+                "mic": [os.path.join(mic_dir, name_of[i]) for i in chunk],
+                "extra": {"nearend_speech": sub("nearend_speech", "nearend_speech"), "echo": sub("echo", "echo")}}
+
+    return _single_file(args, ids, paths_of, dict(VAL_KEYS), h5, runner, batch, filename, "tt_list2.txt", names,
+                        decode_threads, pinned, stats, echo_shape_of_near=True)
+
+
+def create_h5(args, **kw):
+    """The one name all three reference scripts export.  ``args.train_path`` -> the train form; ``args.val_path``
+    -> the val form when it holds the per-signal sub-directories of val_wav2h5.py:11-14, else the test form."""
+    if getattr(args, "train_path", None):
+        return create_h5_train(args, **kw)
+    if getattr(args, "val_path", None):
+        if os.path.isdir(os.path.join(args.val_path, "nearend_mic")):
+            return create_h5_val(args, **kw)
+        return create_h5_test(args, **kw)
+    raise ValueError("args needs train_path (train_wav2h5.py) or val_path (test_wav2h5.py / val_wav2h5.py)")
+
+
 def build_parser(kind: str) -> argparse.ArgumentParser:
-    """The reference's flags and defaults (train_wav2h5.py:55-73, test_wav2h5.py:67-86)."""
+    """The reference's flags and defaults (train_wav2h5.py:55-73, test_wav2h5.py:67-86, val_wav2h5.py:62-86)."""
     p = argparse.ArgumentParser(description=f"wav -> h5 ({kind}) with the stage-1 echo canceller",
                                 formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     if kind == "train":
         p.add_argument("--train_path", type=str, default="/data/lihaoming/datasets/synthetic/train_set")
+        p.add_argument("--h5_path", type=str, default="/data/lihaoming/datasets/synthetic/h5")
+    elif kind == "val":
+        p.add_argument("--val_path", type=str, default="/data/lihaoming/gen_data/data/test_sets")
+        p.add_argument("--h5_path", type=str, default="/data/lihaoming/gen_data/data/h5")
     else:
         p.add_argument("--val_path", type=str, default="/data/lihaoming/datasets/synthetic/test_set")
-    p.add_argument("--h5_path", type=str, default="/data/lihaoming/datasets/synthetic/h5")
+        p.add_argument("--h5_path", type=str, default="/data/lihaoming/datasets/synthetic/h5")
     p.add_argument("--list_path", type=str, default="../examples/filelists")
     p.add_argument("--sr", type=int, default=16000)
     return p
@@ -217,4 +472,4 @@ def build_parser(kind: str) -> argparse.ArgumentParser:
 def main(kind: str = "train", argv=None):
     args = build_parser(kind).parse_args(argv)
     os.makedirs(args.h5_path, exist_ok=True)
-    return create_h5_train(args) if kind == "train" else create_h5_test(args)
+    return {"train": create_h5_train, "test": create_h5_test, "val": create_h5_val}[kind](args)

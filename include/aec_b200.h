@@ -59,7 +59,7 @@ typedef struct aec_cfg {
     float kalman_eps;       /* floor added to the innovation power (default 1e-10) */
     int32_t erle_skip_hops; /* hops excluded from the ERLE sums at the start of each utterance */
     int32_t variant;        /* 0 = library default; otherwise 1000*warps_per_utterance + register cap */
-    int32_t stagger_ns;     /* tuning: start-up skew between co-resident utterances; 0 = default, -1 = off */
+    int32_t stagger_ns;     /* tuning: start-up skew (ns per resident slot) between co-resident utterances; <= 0 = off (default) */
     int32_t reserved[4];
 } aec_cfg;
 
@@ -67,6 +67,11 @@ int aec_version(void);
 const char* aec_strerror(int code);
 /* text of the last CUDA error seen by the calling thread ("" if none) */
 const char* aec_last_cuda_error(void);
+
+/* Optional: builds the constant tables (windows, twiddles) of the CURRENT device now instead of on the first
+ * launch.  Call it once per device before capturing a CUDA graph around the `*_run` entries (the first-use
+ * path allocates and copies, which a capture does not allow). */
+int aec_init(void);
 
 /* fills *cfg with the frozen defaults for the given frame length */
 int aec_cfg_default(aec_cfg* cfg, int32_t frame);
@@ -98,7 +103,17 @@ int aec_stage1_run(const float* far, const float* mic, float* err, float* echo_e
  * pinned host memory (aec_host_alloc) gives full PCIe rate.
  * n_samples is a HOST int64 [B] or NULL. */
 typedef struct aec_host_ctx aec_host_ctx;
+/* A context belongs to the device that was current when it was created (calls made with another device current
+ * return AEC_EINVAL) and is NOT re-entrant: one `aec_stage1_run_host*` call at a time per context; use one
+ * context per thread.  On any failure the call returns only after every copy it started has finished, so the
+ * caller's buffers are never written after the return.
+ * aec_host_ctx_create == aec_host_ctx_create_ex(.., slots = 0, flags = 0). */
 int aec_host_ctx_create(aec_host_ctx** ctx, int64_t slice_utterances, int64_t max_samples);
+/* slots: slices in flight, 1..8 (0 = default 4).  flags: AEC_HOST_CTX_NO_RAMP keeps the first slices full-size
+ * (by default the first slices grow 16, 16, 32, 64, .. so that the first download starts early). */
+enum { AEC_HOST_CTX_NO_RAMP = 1 };
+int aec_host_ctx_create_ex(aec_host_ctx** ctx, int64_t slice_utterances, int64_t max_samples, int32_t slots,
+                           int32_t flags);
 int aec_host_ctx_destroy(aec_host_ctx* ctx);
 int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const float* mic, float* err, float* echo_est,
                         float* erle_db, const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride,
@@ -109,9 +124,16 @@ int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const float* mic, f
 int aec_stage1_run_host_pcm16(aec_host_ctx* ctx, const int16_t* far, const int16_t* mic, float* err,
                               float* echo_est, float* erle_db, const int64_t* n_samples, int64_t B, int64_t L,
                               int64_t in_stride, int64_t out_stride, const aec_cfg* cfg);
-/* page-locked host memory helpers (cudaHostAlloc / cudaFreeHost) */
+/* page-locked host memory helpers (cudaHostAlloc / cudaFreeHost).  Pageable buffers work with the host entries
+ * but every copy is then staged by the driver and serialises the slices -- allocate the arrays that
+ * `librosa.load` results are gathered into with these.  AEC_HOST_WRITE_COMBINED: for buffers the CPU only
+ * writes (inputs); AEC_HOST_PORTABLE: usable from every CUDA context of the process. */
+enum { AEC_HOST_WRITE_COMBINED = 1, AEC_HOST_PORTABLE = 2 };
 int aec_host_alloc(void** ptr, int64_t bytes);
+int aec_host_alloc_ex(void** ptr, int64_t bytes, int32_t flags);
 int aec_host_free(void* ptr);
+/* 1 if ptr lies in page-locked host memory known to CUDA, 0 if not (pageable / unknown) */
+int aec_host_is_pinned(const void* ptr);
 
 /* STFT analysis on DEVICE buffers: replaces ConvSTFT(frame, frame/2, frame, 'hann', 'complex')
  * .forward (Stage2_lhm/scripts/network/attention_ccrn.py:45-52).

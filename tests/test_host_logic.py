@@ -82,7 +82,8 @@ def test_ragged_batching_pads_and_unpads():
 
 class _FakeGroup(dict):
     def create_dataset(self, name, data=None, shape=None, chunks=None):
-        assert chunks is True and shape == data.shape and data.dtype == np.float32
+        assert shape == data.shape and data.dtype == np.float32
+        assert chunks is True or data.size == 0            # h5py rejects chunks=True for an empty dataset
         self[name] = np.array(data)
 
     def create_group(self, name):
@@ -92,7 +93,8 @@ class _FakeGroup(dict):
 
 
 class _FakeH5:
-    files = {}
+    def __init__(self):
+        self.files = {}
 
     def File(self, name, mode):
         assert mode == "w"
@@ -102,43 +104,160 @@ class _FakeH5:
         return f
 
 
-def _write_wavs(folder, ids, n=2000, sr=16000):
+def _write_wavs(folder, ids, n=2000, sr=16000, subdirs=False, dtype=np.int16):
     from scipy.io import wavfile
 
     rng = np.random.default_rng(0)
+    data = {}
     for i in ids:
         for k, pat in wav2h5.WAV_PATTERNS.items():
-            x = (rng.standard_normal(n + 10 * int(i)) * 3000).astype(np.int16)
-            wavfile.write(os.path.join(folder, pat.format(idx=i)), sr, x)
+            if dtype == np.int16:
+                x = (rng.standard_normal(n + 10 * int(i)) * 3000).astype(np.int16)
+            else:
+                x = (rng.standard_normal(n + 10 * int(i)) * 0.1).astype(np.float32)
+            d = os.path.join(folder, k) if subdirs else folder
+            os.makedirs(d, exist_ok=True)
+            wavfile.write(os.path.join(d, pat.format(idx=i)), sr, x)
+            data[(i, k)] = x
+    return data
 
 
-def test_create_h5_train_and_test_schema(tmp_path):
+def _fake_runner(fa, mi, n):          # stand-in for the CUDA runner: like the C ABI it takes float32 or 16-bit PCM
+    if fa.dtype == np.int16:          # (the test wavs are 16-bit, so this is the branch create_h5 takes)
+        fa, mi = fa.astype(np.float32) / np.float32(32768), mi.astype(np.float32) / np.float32(32768)
+    return fa * np.float32(0.5), mi * np.float32(0.25)
+
+
+def test_create_h5_three_forms_schema(tmp_path):
+    """a6: the train / test / val generators (train_wav2h5.py, test_wav2h5.py, val_wav2h5.py) -- file names, keys,
+    list files, stage-1 datasets inside the groups -- and the one `create_h5` name that dispatches to them."""
+    wav_dir, val_dir, h5_dir, list_dir = tmp_path / "wav", tmp_path / "val", tmp_path / "h5", tmp_path / "lists"
+    for d in (wav_dir, val_dir, h5_dir, list_dir):
+        d.mkdir()
+    ids = ["3", "11", "7", "20", "5"]
+    data = _write_wavs(str(wav_dir), ids)
+    fake = _FakeH5()
+    args = types.SimpleNamespace(train_path=str(wav_dir), h5_path=str(h5_dir), list_path=str(list_dir), sr=16000)
+    st = {}
+    paths = wav2h5.create_h5(args, runner=_fake_runner, batch=2, h5=fake, stats=st)       # -> train form
+    assert sorted(os.path.basename(p) for p in paths) == sorted(f"tr_{i}.ex" for i in ids)
+    assert open(list_dir / "tr_list.txt").read().split("\n") == paths
+    assert st["utterances"] == 5 and st["pcm16_batches"] == 3 and st["float32_batches"] == 0
+    for p in paths:
+        f = fake.files[p]
+        idx = os.path.basename(p)[3:-3]
+        assert set(f) == {"nearend_speech", "nearend_mic", "farend_speech", "echo", "stage1_error", "stage1_echo"}
+        for k in wav2h5.KEYS:                                   # exactly what librosa.load gives for a 16-bit wav
+            assert np.array_equal(f[k], data[(idx, k)].astype(np.float32) / np.float32(32768))
+        assert f["stage1_error"].shape == f["farend_speech"].shape
+        assert np.array_equal(f["stage1_error"], np.float32(0.5) * f["farend_speech"])
+        assert np.array_equal(f["stage1_echo"], np.float32(0.25) * f["nearend_mic"])
+    # test form
+    fake = _FakeH5()
+    args = types.SimpleNamespace(val_path=str(wav_dir), h5_path=str(h5_dir), list_path=str(list_dir), sr=16000)
+    path = wav2h5.create_h5(args, runner=_fake_runner, batch=2, h5=fake)                 # -> test form (flat folder)
+    assert os.path.basename(path) == "test.ex"
+    root = fake.files[path]
+    assert sorted(root, key=int) == ["0", "1", "2", "3", "4"]     # ONLY numbered groups at the root (test.py:23)
+    names = open(list_dir / "filename.txt").read().split("\n")
+    assert sorted(names) == sorted(ids)
+    for g, idx in zip(sorted(root, key=int), names):              # group order == filename.txt order
+        assert set(root[g]) == set(wav2h5.KEYS) | {"stage1_error", "stage1_echo"}
+        assert np.array_equal(root[g]["echo"], data[(idx, "echo")].astype(np.float32) / np.float32(32768))
+    assert open(list_dir / "tt_list.txt").read() == path
+    # val form: sub-directory per signal, keys mic/ref/near/echo, tt/test2.ex, tt_list2.txt, basenames in filename.txt
+    vdata = _write_wavs(str(val_dir), ["4", "9", "1"], subdirs=True)
+    fake = _FakeH5()
+    args = types.SimpleNamespace(val_path=str(val_dir), h5_path=str(h5_dir), list_path=str(list_dir), sr=16000)
+    path = wav2h5.create_h5(args, runner=_fake_runner, batch=2, h5=fake)                 # -> val form
+    assert os.path.basename(path) == "test2.ex" and open(list_dir / "tt_list2.txt").read() == path
+    root = fake.files[path]
+    names = open(list_dir / "filename.txt").read().split("\n")
+    assert sorted(names) == sorted(f"nearend_mic_fileid_{i}.wav" for i in ("4", "9", "1"))
+    assert sorted(root, key=int) == ["0", "1", "2"]
+    for g, base in zip(sorted(root, key=int), names):
+        idx = base.split("_")[-1].split(".wav")[0]
+        assert set(root[g]) == {"mic", "ref", "near", "echo", "stage1_error", "stage1_echo"}
+        for out_key, src in wav2h5.VAL_KEYS.items():
+            assert np.array_equal(root[g][out_key], vdata[(idx, src)].astype(np.float32) / np.float32(32768))
+        assert np.array_equal(root[g]["stage1_error"], np.float32(0.5) * root[g]["ref"])
+
+
+def test_create_h5_float_wavs_take_the_float32_path_and_npz_store_round_trips(tmp_path):
     wav_dir, h5_dir, list_dir = tmp_path / "wav", tmp_path / "h5", tmp_path / "lists"
     for d in (wav_dir, h5_dir, list_dir):
         d.mkdir()
-    _write_wavs(str(wav_dir), ["3", "11"])
-    def runner(fa, mi, n):            # stand-in for the CUDA runner: like the C ABI it takes float32 or 16-bit PCM
-        if fa.dtype == np.int16:      # (the test wavs are 16-bit, so this is the branch create_h5 takes)
-            fa, mi = fa.astype(np.float32) / np.float32(32768), mi.astype(np.float32) / np.float32(32768)
-        return fa * np.float32(0.5), mi * np.float32(0.25)
-
-    fake = _FakeH5()
+    data = _write_wavs(str(wav_dir), ["1", "2"], dtype=np.float32)       # IEEE-float wavs: not the PCM16 fast path
     args = types.SimpleNamespace(train_path=str(wav_dir), h5_path=str(h5_dir), list_path=str(list_dir), sr=16000)
-    paths = wav2h5.create_h5_train(args, runner=runner, batch=1, h5=fake)
-    assert sorted(os.path.basename(p) for p in paths) == ["tr_11.ex", "tr_3.ex"]
-    assert open(list_dir / "tr_list.txt").read().split("\n") == paths
+    st = {}
+    paths = wav2h5.create_h5_train(args, runner=_fake_runner, batch=4, h5=wav2h5.NpzStore(), stats=st)
+    assert st["float32_batches"] == 1 and st["pcm16_batches"] == 0
     for p in paths:
-        f = fake.files[p]
-        assert set(f) == {"nearend_speech", "nearend_mic", "farend_speech", "echo", "stage1_error", "stage1_echo"}
-        assert f["stage1_error"].shape == f["farend_speech"].shape
-        assert np.allclose(f["stage1_error"], 0.5 * f["farend_speech"])
-    args = types.SimpleNamespace(val_path=str(wav_dir), h5_path=str(h5_dir), list_path=str(list_dir), sr=16000)
-    path = wav2h5.create_h5_test(args, runner=runner, batch=2, h5=fake)
-    root = fake.files[path]
-    assert sorted(root) == ["0", "1"]                     # ONLY numbered groups at the root (test.py:23)
-    assert "stage1_error" in root["0"] and "nearend_mic" in root["1"]
-    assert open(list_dir / "tt_list.txt").read() == path
-    assert len(open(list_dir / "filename.txt").read().split("\n")) == 2
+        idx = os.path.basename(p)[3:-3]
+        with np.load(p) as z:
+            assert set(z.files) == set(wav2h5.KEYS) | {"stage1_error", "stage1_echo"}
+            assert np.array_equal(z["farend_speech"], data[(idx, "farend_speech")])
+            assert np.array_equal(z["stage1_error"], np.float32(0.5) * z["farend_speech"])
+
+
+def test_wav_probe_and_pcm16_fast_read(tmp_path):
+    from scipy.io import wavfile
+
+    from acoustic_echo_cancellation_b200 import ingest
+
+    x = (np.random.default_rng(1).standard_normal(1234) * 5000).astype(np.int16)
+    p = str(tmp_path / "a.wav")
+    wavfile.write(p, 16000, x)
+    info = ingest.probe_wav(p)
+    assert (info.rate, info.channels, info.bits, info.fmt, info.frames) == (16000, 1, 16, 1, 1234)
+    assert info.fast(16000) and not info.fast(8000)
+    row = np.full(2000, 7, dtype=np.int16)
+    assert ingest.read_pcm16_into(p, info, row) == 1234
+    assert np.array_equal(row[:1234], x) and (row[1234:] == 0).all()
+    assert np.array_equal(ingest.pcm16_to_float32(x), ingest.load_wav(p, 16000))     # == librosa's x / 32768
+    wavfile.write(p, 16000, np.stack([x, x], axis=1))
+    assert not ingest.probe_wav(p).fast(16000)                   # stereo -> general loader
+    with open(str(tmp_path / "bad.wav"), "wb") as f:
+        f.write(b"not a wav file at all")
+    with pytest.raises(ValueError):
+        ingest.probe_wav(str(tmp_path / "bad.wav"))
+    # ragged microphone: shorter than the far end is zero-padded, longer is cut on upload but stored in full
+    far, mic_short, mic_long = str(tmp_path / "f.wav"), str(tmp_path / "ms.wav"), str(tmp_path / "ml.wav")
+    wavfile.write(far, 16000, x)
+    wavfile.write(mic_short, 16000, x[:1000])
+    wavfile.write(mic_long, 16000, np.concatenate([x, x[:50]]))
+    dec = ingest.BatchDecoder(16000, threads=2)
+    b = dec.decode([far, far], [mic_short, mic_long], {"echo": [far, far]})
+    assert b.pcm16 and b.n.tolist() == [1234, 1234] and b.far.shape == (2, 1234)
+    assert np.array_equal(b.mic[0, :1000], x[:1000]) and (b.mic[0, 1000:] == 0).all()
+    assert np.array_equal(b.mic[1], x)
+    assert len(b.signals["__mic__"][0]) == 1000 and len(b.signals["__mic__"][1]) == 1284
+    dec.close()
+
+
+def _shard_worker(rank, world, port, folder, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ids = wav2h5.list_utterance_ids(folder)
+    if rank == 1:
+        ids = ids[::-1]                       # ranks may see the directory in different orders
+    mine, r = wav2h5._shard(ids)
+    ret[rank] = list(mine)
+    dist.destroy_process_group()
+
+
+def test_two_rank_shards_are_disjoint_and_complete(tmp_path):
+    ids = [str(i) for i in (12, 3, 100, 7, 45, 9, 1)]
+    _write_wavs(str(tmp_path), ids, n=64)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_shard_worker, args=(2, port, str(tmp_path), ret), nprocs=2, join=True)
+    a, b = ret[0], ret[1]
+    assert not (set(a) & set(b)) and sorted(a + b, key=int) == sorted(ids, key=int)
+    assert abs(len(a) - len(b)) <= 1
+    assert a + b == sorted(ids, key=int)      # numeric order of the ids: contiguous shards of one sorted list
 
 
 def test_cli_flags_match_the_reference():
@@ -148,6 +267,9 @@ def test_cli_flags_match_the_reference():
         "../examples/filelists", 16000)
     b = wav2h5.build_parser("test").parse_args(["--val_path", "x", "--sr", "8000"])
     assert b.val_path == "x" and b.sr == 8000
+    c = wav2h5.build_parser("val").parse_args([])              # val_wav2h5.py:66-84
+    assert (c.val_path, c.h5_path, c.sr) == ("/data/lihaoming/gen_data/data/test_sets",
+                                             "/data/lihaoming/gen_data/data/h5", 16000)
 
 
 def test_cpulist_parser_and_bind_is_harmless_without_gpu():
