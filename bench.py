@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- audio-seconds per second of the stage-1 STFT + FDAF echo canceller on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4]
     (N > 1: launched by torchrun, one rank per GPU)
 
 One "step" = one pass of the hot path over one batch of synthetic utterances:
@@ -9,8 +9,12 @@ One "step" = one pass of the hot path over one batch of synthetic utterances:
             hop 256, 4-partition FDAF-NLMS  (weak scaling: every rank owns its own 1024).
   value     whole-job audio-seconds processed per second, inputs resident in HBM, device-timed
             (CUDA events on the launching stream, max over ranks).
-  e2e       same metric through the host-buffer C-ABI call (aec_stage1_run_host): pinned host
-            inputs -> H2D -> kernel -> D2H of the error signal, all inside the timed region.
+  e2e       same metric through the host-buffer C-ABI call with page-locked HOST buffers: H2D -> kernel ->
+            D2H of the error signal, all inside the timed region.  Headline = the 16-bit PCM entry
+            (aec_stage1_run_host_pcm16: what the wav corpus holds and what create_h5 feeds); the float32
+            entry (aec_stage1_run_host) is reported beside it as `float32_variant`.
+  also      (N = 1) configs[2], configs[3] and the many-wave batch, device-timed the same way, outside the
+            headline's timed region.
   roofline  the fused stage-1 kernel against the MEASURED FP32 FFMA peak of this GPU (binding
             roofline) with the HBM fraction (MEASURED_PEAKS.json) beside it.
   cpu_baseline  the C oracle (builder-authored port; the reference has no stage-1 filter) on the
@@ -123,44 +127,53 @@ def measured_peaks():
     return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
-def make_inputs_device(torch, B, L, seed, P, SR=16000, hop=256):
-    """SURVEY.md 8d recipe on the device (seeded): speech-like far end, exponentially decaying random
-    RIR of P*256 taps, mic = echo + noise at -40 dB.  Untimed set-up."""
-    g = torch.Generator(device="cuda").manual_seed(seed)
-    far = torch.empty(B, L, device="cuda")
-    mic = torch.empty(B, L, device="cuda")
-    t = torch.arange(L, device="cuda", dtype=torch.float32) / SR
+def make_inputs(torch, B, L, seed, P, SR=16000, hop=256, device="cuda", draws="host"):
+    """SURVEY.md 8d recipe (seeded): speech-like far end, exponentially decaying random RIR of P*hop taps,
+    mic = echo + noise at -40 dB.  ONE generator for both arms: the Gaussian draws come from a CPU
+    torch.Generator (utterance block b0 uses seed + b0, so the first k utterances are the same whatever B is),
+    the filtering runs on `device` -- the GPU for our arm, the host for `--impl reference`.  Untimed set-up."""
+    far = torch.empty(B, L, device=device)
+    mic = torch.empty(B, L, device=device)
+    t = torch.arange(L, device=device, dtype=torch.float32) / SR
     env = 0.5 - 0.5 * torch.cos(2 * torch.pi * 4.0 * t)
     nfft = 1 << (L + P * hop).bit_length()
-    lp = torch.fft.rfft(0.9 ** torch.arange(128, device="cuda", dtype=torch.float32), n=nfft)
+    lp = torch.fft.rfft(0.9 ** torch.arange(128, device=device, dtype=torch.float32), n=nfft)
     tau = P * hop / 6.9
-    dec = torch.exp(-torch.arange(P * hop, device="cuda", dtype=torch.float32) / tau)
+    dec = torch.exp(-torch.arange(P * hop, device=device, dtype=torch.float32) / tau)
     step = 64 if L <= 200000 else 16
+    pin = device != "cpu"
     for b0 in range(0, B, step):
         nb = min(step, B - b0)
-        x = torch.randn(nb, L, device="cuda", generator=g)
+        if draws == "device":      # side measurements only: same recipe, draws from the device generator
+            g = torch.Generator(device=device).manual_seed(seed * 100003 + b0)
+            dr = torch.randn(nb, 2 * L + P * hop, generator=g, device=device)
+        else:
+            g = torch.Generator(device="cpu").manual_seed(seed * 100003 + b0)
+            dr = torch.randn(nb, 2 * L + P * hop, generator=g, pin_memory=pin).to(device, non_blocking=True)
+        x = dr[:, :L]
         x = torch.fft.irfft(torch.fft.rfft(x, n=nfft) * lp, n=nfft)[:, :L] * env
         x = 0.5 * x / x.abs().amax(dim=1, keepdim=True)
-        h = torch.randn(nb, P * hop, device="cuda", generator=g) * dec
+        h = dr[:, 2 * L:] * dec
         h = 0.5 * h / h.norm(dim=1, keepdim=True)
         echo = torch.fft.irfft(torch.fft.rfft(x, n=nfft) * torch.fft.rfft(h, n=nfft), n=nfft)[:, :L]
-        noise = torch.randn(nb, L, device="cuda", generator=g) * echo.pow(2).mean(dim=1, keepdim=True).sqrt() * 0.01
+        noise = dr[:, L:2 * L] * echo.pow(2).mean(dim=1, keepdim=True).sqrt() * 0.01
         far[b0:b0 + nb] = x
         mic[b0:b0 + nb] = echo + noise
     return far, mic
 
 
-def make_inputs_host(np, B, L, seed):
-    """Host-only inputs for the CPU arm (no GPU needed): same shape/scale, numpy PCG64."""
-    rng = np.random.default_rng(seed)
-    far = (0.15 * rng.standard_normal((B, L))).astype(np.float32)
-    h = (rng.standard_normal(64) * np.exp(-np.arange(64) / 10.0)).astype(np.float32)
-    h *= 0.5 / np.linalg.norm(h)
-    mic = np.empty_like(far)
-    for b in range(B):
-        mic[b] = np.convolve(far[b], h)[:L]
-    mic += (0.001 * rng.standard_normal((B, L))).astype(np.float32)
-    return far, mic
+def workload_config(wl, world):
+    """`config` of the JSON line -- identical for both arms."""
+    B, L, SR, FRAME = wl["B"], wl["L"], wl["sr"], wl["frame"]
+    return {"workload": wl["name"], "utterances_per_gpu": B, "samples": L, "sample_rate": SR,
+            "frame": FRAME, "hop": FRAME // 2, "partitions": wl["P"], "algo": "nlms" if wl["algo"] == 0 else "kalman",
+            "generator": "bench.make_inputs (SURVEY 8d recipe, CPU-seeded draws, seed 1000 + rank)",
+            "l2": "inputs %.1f GB/GPU per step >> 126 MB L2 (no flush needed)" % (2 * B * L * 4 / 1e9),
+            "parallelism": f"utterance-sharded x{world}, metrics-only all_gather"}
+
+
+def cpu_sample_size(cores, B):
+    return int(min(512, max(32, 16 * cores), B))
 
 
 def cpu_arm(np, far, mic, wl, steps, warmup):
@@ -185,30 +198,192 @@ def cpu_arm(np, far, mic, wl, steps, warmup):
     return far.shape[0] * far.shape[1] / wl["sr"] / dt, threads, dt * 1e3
 
 
+def stft_shell_cpu(np, far, mic, frame, threads):
+    """The reference's own STFT shell on the host cores: ConvSTFT x 2 +
+    ConviSTFT x 1 (Stage2_lhm/scripts/network/attention_ccrn.py:28-101) -- dense strided convolutions.  The
+    reference modules themselves are timed when /root/reference is present (this container); on the GPU box it is
+    not, and the same dense-conv formulation restated with torch.nn.functional is timed instead (kind "port")."""
+    import torch
+    import torch.nn.functional as F
+
+    torch.set_num_threads(max(1, threads))
+    hop = frame // 2
+    x, y = torch.from_numpy(far), torch.from_numpy(mic)
+    ref_dir = "/root/reference/Stage2_lhm/scripts"
+    kind = "port"
+    stft = istft = None
+    if os.path.isdir(ref_dir):
+        try:
+            sys.path.insert(0, ref_dir)
+            from network.attention_ccrn import ConvSTFT, ConviSTFT  # type: ignore
+
+            stft = ConvSTFT(frame, hop, frame, "hann", "complex", fix=True)
+            istft = ConviSTFT(frame, hop, frame, "hann", "complex", fix=True)
+            kind = "reference"
+        except Exception:
+            stft = istft = None
+        finally:
+            sys.path.remove(ref_dir)
+    if stft is None:
+        w = torch.hann_window(frame, periodic=True, dtype=torch.float64)
+        basis = torch.fft.rfft(torch.eye(frame, dtype=torch.float64))
+        k = torch.cat([basis.real, basis.imag], 1).T
+        kf = (k * w)[:, None, :].float()
+        ki = (torch.linalg.pinv(k).T * w)[:, None, :].float()
+        eye = torch.eye(frame)[:, None, :]
+        wf = w.float()
+
+        def stft(v):
+            return F.conv1d(F.pad(v[:, None, :], [frame - hop, frame - hop]), kf, stride=hop)
+
+        def istft(sp):
+            o = F.conv_transpose1d(sp, ki, stride=hop)
+            tt = (wf[None, :, None] ** 2).repeat(1, 1, sp.size(-1))
+            coff = F.conv_transpose1d(tt, eye, stride=hop)
+            return (o / (coff + 1e-8))[..., frame - hop:-(frame - hop)]
+
+    with torch.no_grad():
+        istft(stft(x[:2]) - stft(y[:2]))                      # warm-up
+        t0 = time.perf_counter()
+        istft(stft(y) - stft(x))
+        dt = time.perf_counter() - t0
+    return {"kind": kind, "seconds": dt, "utterances": int(far.shape[0]), "threads": threads,
+            "what": "ConvSTFT x 2 + ConviSTFT x 1 only (no filter): attention_ccrn.py:28-101"}
+
+
 def run_reference(args, wl):
     """`--impl reference`: the CPU arm.  The reference repository has no implementation of this
-    path (no FDAF at all), so the arm is the builder-authored C port on the host cores."""
+    path (no FDAF at all), so the arm is the builder-authored C port on the host cores, on the first utterances
+    of the SAME generator, seed and configuration as our arm."""
     import numpy as np
+    import torch
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = int(min(512, max(32, 16 * cores)))
-    far, mic = make_inputs_host(np, sample, wl["L"], 99)
+    sample = cpu_sample_size(cores, wl["B"])
+    torch.set_num_threads(cores)
+    far, mic = make_inputs(torch, sample, wl["L"], 1000, wl["P"], wl["sr"], wl["frame"] // 2, device="cpu")
+    far, mic = far.numpy(), mic.numpy()
     v, threads, ms = cpu_arm(np, far, mic, wl, args.steps, max(args.warmup, 1))
+    shell = None
+    try:
+        n_shell = min(sample, 64)
+        sh = stft_shell_cpu(np, far[:n_shell], mic[:n_shell], wl["frame"], threads)
+        sh["audio_s_per_s"] = n_shell * wl["L"] / wl["sr"] / sh["seconds"]
+        shell = sh
+    except Exception as e:      # the shell figure is context, never the arm's value
+        shell = {"unavailable": repr(e)}
     line = {
         "impl": "reference", "metric": "audio_seconds_per_second_stage1_aec", "value": v, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "sample": f"{sample} utterances x 10 s per step"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (seeded: speech-like far end, random decaying RIR, -40 dB noise)",
+        "config": workload_config(wl, args.gpus),
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} x 10 s utterances per step, C oracle (oracle/csrc/aec_oracle.c), "
-                                   f"OpenMP over utterances; the reference has no CPU FDAF to time"},
+                         "sample": f"first {sample} utterances x {wl['L'] / wl['sr']:.0f} s of the workload per step, C "
+                                   f"oracle (oracle/csrc/aec_oracle.c, builder-authored port: the reference has no CPU "
+                                   f"FDAF to time), OpenMP over utterances",
+                         "reference_stft_shell": shell},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "parity": "FDAF recurrence: parity UNPINNED (no reference implementation); STFT/iSTFT pinned by golden vectors",
     }
     print(json.dumps(line), flush=True)
+
+
+def device_timed(A, torch, dist, sharding, far, mic, err, cfg, steps, world, n_total):
+    """K steps of the device-resident path, CUDA events on the launching stream (whole region and per launch);
+    returns (total_ms, mean_kernel_ms, launches, last erle, wall window)."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    A.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    wall0 = time.perf_counter()
+    ev0.record()
+    pending = []
+    erle = None
+    for i in range(steps):
+        kev[i][0].record()
+        erle = A.stage1_aec(far, mic, cfg, out=err, return_erle=True)[1]
+        kev[i][1].record()
+        if world > 1:     # metrics gather of step i runs on NCCL's stream under the kernel of step i + 1
+            pending.append(sharding.gather_metrics(erle, n_total, async_op=True))
+    for _, work in pending:
+        if work is not None:
+            work.wait()   # every step's gathered metrics are complete inside the timed region
+    ev1.record()
+    barrier()
+    wall1 = time.perf_counter()
+    launches = A.launch_count()
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / steps
+    return total_ms, kern_ms, launches, erle, (wall0, wall1)
+
+
+def roofline_of(wl, kern_ms, fp32_peak, hbm_peak, hbm_src, traffic=None):
+    frames = wl["L"] // (wl["frame"] // 2) + 1
+    flops_launch = flops_per_frame(wl["frame"], wl["P"], wl["algo"]) * frames * wl["B"]
+    bytes_launch = 3 * 4 * wl["L"] * wl["B"]
+    tf = flops_launch / (kern_ms * 1e-3) / 1e12
+    gbs = bytes_launch / (kern_ms * 1e-3) / 1e9
+    return {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
+            "traffic": traffic, "kernel": "aec::stage1_n%d_kernel" % wl["frame"], "kernel_ms": kern_ms,
+            "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
+            "peak_source": "FFMA probe measured live in this run (aec_bench_fp32_peak; FFMAs with constant operands -- "
+                           "FFMAs with three register sources issue at 0.64 of it, profiles/r2_ffma_reuse.txt); "
+                           "MEASURED_PEAKS.json carries no FP32 figure",
+            "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}}
+
+
+def also_rows(A, torch, sharding, args, fp32_peak, hbm_peak, hbm_src, local):
+    """Outside the headline's timed region (N = 1 only): the other single-GPU configurations of BASELINE.json and
+    the many-wave batch, device-timed with the same method, so that they exist in the driver's record."""
+    rows = []
+    extra = [dict(WORKLOADS[3]), dict(WORKLOADS[4]),
+             dict(WORKLOADS[2], B=4144, name="many waves: 4144 x 10 s utterances (28 per SM), 16 kHz, 4-partition FDAF-NLMS")]
+    for wl in extra:
+        try:
+            far, mic = make_inputs(torch, wl["B"], wl["L"], 7, wl["P"], wl["sr"], wl["frame"] // 2, device="cuda",
+                                   draws="device")
+            err = torch.empty_like(far)
+            cfg = A.Stage1Config(frame=wl["frame"], partitions=wl["P"], algo=wl["algo"], erle_skip_hops=125)
+            for _ in range(3):
+                A.stage1_aec(far, mic, cfg, out=err, return_erle=True)
+            torch.cuda.synchronize()
+            sampler = ClockSampler(local)
+            sampler.start()
+            time.sleep(0.1)
+            load0 = time.perf_counter()
+            steps = max(5, min(args.steps, 20))
+            total_ms, kern_ms, launches, erle, (w0, w1) = device_timed(A, torch, None, sharding, far, mic, err, cfg, steps,
+                                                                      1, wl["B"])
+            while time.perf_counter() - load0 < 0.35:          # keep the same load up until the sampler has >= 3 samples
+                A.stage1_aec(far, mic, cfg, out=err, return_erle=True)
+                torch.cuda.synchronize()
+            load1 = time.perf_counter()
+            time.sleep(0.05)
+            sampler.stop()
+            ms = total_ms / steps
+            rf = roofline_of(wl, kern_ms, fp32_peak, hbm_peak, hbm_src)
+            rows.append({"workload": wl["name"], "ms_per_step": ms, "steps": steps,
+                         "value": wl["B"] * wl["L"] / wl["sr"] / (ms * 1e-3), "unit": "audio-s/s",
+                         "roofline": {"frac": rf["frac"], "achieved": rf["achieved"], "peak": rf["peak"], "unit": rf["unit"],
+                                      "hbm_frac": rf["hbm"]["frac"], "kernel_ms": kern_ms},
+                         "gpu_launches": int(launches), "erle_db_mean": float(erle.float().mean()),
+                         "outputs_finite": bool(torch.isfinite(err).all()),
+                         "clocks": sampler.summary(w0, w1, load0, load1)})
+            del far, mic, err
+            torch.cuda.empty_cache()
+        except Exception as e:                                  # never lose the headline line to a side measurement
+            rows.append({"workload": wl["name"], "error": repr(e)})
+    return rows
 
 
 def main():
@@ -221,7 +396,10 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--e2e-slots", type=int, default=0)
+    ap.add_argument("--e2e-slice", type=int, default=128)
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
     if args.impl == "reference":
@@ -251,7 +429,7 @@ def main():
     B, L, P, algo = wl["B"], wl["L"], wl["P"], wl["algo"]
     SR, FRAME = wl["sr"], wl["frame"]
     HOP = FRAME // 2
-    far, mic = make_inputs_device(torch, B, L, 1000 + rank, P, SR, HOP)
+    far, mic = make_inputs(torch, B, L, 1000 + rank, P, SR, HOP, device="cuda")
     err = torch.empty_like(far)
     cfg = A.Stage1Config(frame=FRAME, partitions=P, algo=algo, erle_skip_hops=125, variant=args.variant)
     n_total = B * world
@@ -281,27 +459,9 @@ def main():
     load0 = time.perf_counter()
     for _ in range(max(3, int(0.15 / 0.002))):      # ~0.15 s of identical launches so the sampler sees load
         A.stage1_aec(far, mic, cfg, out=err, return_erle=True)
-    barrier()
-    A.launch_count(reset=True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    wall0 = time.perf_counter()
-    ev0.record()
-    pending = []
-    for i in range(args.steps):
-        kev[i][0].record()
-        erle = A.stage1_aec(far, mic, cfg, out=err, return_erle=True)[1]
-        kev[i][1].record()
-        if world > 1:     # metrics gather of step i runs on NCCL's stream under the kernel of step i + 1
-            pending.append(sharding.gather_metrics(erle, n_total, async_op=True))
-    for erle, work in pending:
-        if work is not None:
-            work.wait()   # every step's gathered metrics are complete inside the timed region
-    ev1.record()
-    barrier()
-    wall1 = time.perf_counter()
+    total_ms, kern_ms, launches, erle, (wall0, wall1) = device_timed(A, torch, dist, sharding, far, mic, err, cfg,
+                                                                    args.steps, world, n_total)
     wall = wall1 - wall0
-    launches = A.launch_count()
     clocks = None
     if rank == 0:
         if wall < 0.3:                               # keep the GPU under the same load while sampling
@@ -314,8 +474,6 @@ def main():
         sampler.stop()
         clocks = sampler.summary(wall0, wall1, load0, load1)
     barrier()
-    total_ms = ev0.elapsed_time(ev1)
-    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     tmax = torch.tensor([total_ms, kern_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -326,54 +484,63 @@ def main():
     erle_mean = float(erle.float().mean())
     finite = bool(torch.isfinite(err).all())
 
-    # ---- e2e: pinned host buffers through aec_stage1_run_host, copies inside the timed region ----
+    # ---- e2e: page-locked HOST buffers through the host-buffer C ABI, copies inside the timed region ----
+    # headline: the 16-bit PCM entry (aec_stage1_run_host_pcm16) -- the wav files of the reference's generators hold
+    # 16-bit PCM and `create_h5` feeds them to this entry as such (tests: bit-identical to the float32 entry on
+    # x / 32768); the float32 entry (what a caller holding librosa.load's arrays uses) is reported beside it.
     e2e = None
+    e2e_match = None
+    hf = hm = None
     if not args.no_e2e:
         hf, hm, he = A.pinned_empty((B, L)), A.pinned_empty((B, L)), A.pinned_empty((B, L))
         herle = np.empty(B, dtype=np.float32)
         hf[:] = far.cpu().numpy()
         hm[:] = mic.cpu().numpy()
-        pipe = A.HostPipeline(slice_utterances=min(128, B), max_samples=L, device=local)
-        for _ in range(2):
-            pipe.run(hf, hm, cfg, err=he, erle=herle)
-        barrier()
+        sl = min(args.e2e_slice, B)
+        pipe = A.HostPipeline(slice_utterances=sl, max_samples=L, device=local, slots=args.e2e_slots)
         k_e2e = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            pipe.run(hf, hm, cfg, err=he, erle=herle)     # returns when the outputs are in host memory
-        barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": audio_s_step / float(dt[0]), "unit": "audio-s/s",
-               "h2d_bytes_per_step": 2 * B * L * 4, "d2h_bytes_per_step": B * L * 4 + B * 4,
-               "ms_per_step": float(dt[0]) * 1e3, "steps": k_e2e,
-               "api": "aec_stage1_run_host (HostPipeline.run), float32 pinned host memory, 128-utterance slices (tapered at "
-                      "the end), 4 slices in flight; PCIe-bound (H2D %.2f GB/step at ~50 GB/s with D2H running)" % (2 * B * L * 4 / 1e9)}
-        e2e_match = bool(np.array_equal(he, err.cpu().numpy()))
-        # wav-ingest variant: 16-bit PCM host buffers (what the wav files hold), converted on the GPU
+
+        def time_host(a, b):
+            for _ in range(2):
+                pipe.run(a, b, cfg, err=he, erle=herle)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                pipe.run(a, b, cfg, err=he, erle=herle)     # returns when the outputs are in host memory
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt[0])
+
+        dt32 = time_host(hf, hm)
+        e2e_match32 = bool(np.array_equal(he, err.cpu().numpy()))
+        f32_variant = {"value": audio_s_step / dt32, "unit": "audio-s/s",
+                       "h2d_bytes_per_step": 2 * B * L * 4, "d2h_bytes_per_step": B * L * 4 + B * 4,
+                       "ms_per_step": dt32 * 1e3, "bitwise_equal_to_device_path": e2e_match32,
+                       "api": "aec_stage1_run_host: float32 page-locked host memory in (H2D %.2f GB/step)" % (2 * B * L * 4 / 1e9)}
         h16f = A.pinned_empty((B, L), dtype=np.int16)
         h16m = A.pinned_empty((B, L), dtype=np.int16)
         h16f[:] = np.clip(np.rint(hf * 32768.0), -32768, 32767).astype(np.int16)
         h16m[:] = np.clip(np.rint(hm * 32768.0), -32768, 32767).astype(np.int16)
-        for _ in range(2):
-            pipe.run(h16f, h16m, cfg, err=he, erle=herle)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            pipe.run(h16f, h16m, cfg, err=he, erle=herle)
-        barrier()
-        dt16 = torch.tensor([(time.perf_counter() - t0) / k_e2e], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt16, op=dist.ReduceOp.MAX)
-        e2e["pcm16_variant"] = {"value": audio_s_step / float(dt16[0]), "unit": "audio-s/s",
-                                "h2d_bytes_per_step": 2 * B * L * 2, "d2h_bytes_per_step": B * L * 4 + B * 4,
-                                "ms_per_step": float(dt16[0]) * 1e3,
-                                "api": "aec_stage1_run_host_pcm16: int16 PCM in (wav sample format), float32 out"}
+        dt16 = time_host(h16f, h16m)
+        he16 = he.copy()
+        # the float32 entry on the de-quantised samples must give the same bits
+        hf[:] = h16f.astype(np.float32) * np.float32(1.0 / 32768.0)
+        hm[:] = h16m.astype(np.float32) * np.float32(1.0 / 32768.0)
+        pipe.run(hf, hm, cfg, err=he, erle=herle)
+        e2e_match = bool(np.array_equal(he, he16))
+        hf[:] = far.cpu().numpy()
+        hm[:] = mic.cpu().numpy()
+        e2e = {"value": audio_s_step / dt16, "unit": "audio-s/s",
+               "h2d_bytes_per_step": 2 * B * L * 2, "d2h_bytes_per_step": B * L * 4 + B * 4,
+               "ms_per_step": dt16 * 1e3, "steps": k_e2e, "per_gpu": audio_s_step / dt16 / world,
+               "api": "aec_stage1_run_host_pcm16 (HostPipeline.run): int16 PCM (the wav sample format) in page-locked host "
+                      "memory -> H2D -> x/32768 on the GPU -> stage-1 kernel -> D2H of the float32 error signal + ERLE; "
+                      "%d-utterance slices (ramped / tapered), %d slices in flight" % (sl, args.e2e_slots or 4),
+               "bitwise_equal_to_float32_entry": e2e_match,
+               "float32_variant": f32_variant}
         pipe.close()
-    else:
-        hf = hm = None
-        e2e_match = None
 
     if rank != 0:
         if world > 1:
@@ -381,12 +548,7 @@ def main():
         return
 
     # ---- roofline of the dominant (only) kernel ----
-    frames = L // HOP + 1
-    flops_launch = flops_per_frame(FRAME, P, algo) * frames * B
-    bytes_launch = 3 * 4 * L * B
     hbm_peak, hbm_src = measured_peaks()
-    tf = flops_launch / (kern_ms * 1e-3) / 1e12
-    gbs = bytes_launch / (kern_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -394,54 +556,40 @@ def main():
             traffic = json.load(open(tpath)).get(f"config{args.config}")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
-                "traffic": traffic, "kernel": "aec::stage1_n%d_kernel" % FRAME, "kernel_ms": kern_ms,
-                "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
-                "peak_source": "FFMA probe measured live in this run (aec_bench_fp32_peak); "
-                               "MEASURED_PEAKS.json carries no FP32 figure",
-                "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                        "peak_source": hbm_src}}
-
-    if args.config == 2:
-        # context for `frac` (static analysis of the measured SASS, profiles/r1_fp32_issue_rates.txt): FFMAs with three
-        # distinct register sources issue at 0.64 per cycle per scheduler on this part; with them counted at that rate the
-        # instruction stream of this kernel cannot exceed ~9.1 M audio-s/s per GPU (0.44 of the FFMA peak)
-        ceiling = 9.1e6
-        roofline["issue_limited_ceiling"] = {"audio_s_per_s_per_gpu": ceiling, "frac_of_ceiling": (value / world) / ceiling,
-                                             "source": "profiles/r1_fp32_issue_rates.txt, DESIGN.md section 5 (Roofline)"}
+    roofline = roofline_of(wl, kern_ms, fp32_peak, hbm_peak, hbm_src, traffic)
 
     # ---- CPU baseline: the C port on this box's cores, bounded sample of the same workload ----
     cpu = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = int(min(512, max(32, 16 * cores), B))
-        if hf is not None:
-            sf, sm_ = np.array(hf[:sample]), np.array(hm[:sample])
-        else:
-            sf, sm_ = far[:sample].cpu().numpy(), mic[:sample].cpu().numpy()
+        sample = cpu_sample_size(cores, B)
+        sf, sm_ = far[:sample].cpu().numpy(), mic[:sample].cpu().numpy()
         v, threads, _ = cpu_arm(np, sf, sm_, wl, 2, 1)
         cpu = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
-               "sample": f"first {sample} utterances x 10 s of the same workload, 2 timed passes, C oracle "
+               "sample": f"first {sample} utterances x {L / SR:.0f} s of the same workload, 2 timed passes, C oracle "
                          f"(builder-authored port: the reference has no stage-1 filter), OpenMP over utterances"}
+
+    also = None
+    if world == 1 and args.config == 2 and not args.no_also:
+        del far, mic, err
+        torch.cuda.empty_cache()
+        also = also_rows(A, torch, sharding, args, fp32_peak, hbm_peak, hbm_src, local)
 
     line = {
         "metric": "audio_seconds_per_second_stage1_aec", "value": value, "unit": "audio-s/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic (seeded on device: speech-like far end, random decaying RIR, -40 dB noise)",
-        "config": {"workload": wl["name"], "utterances_per_gpu": B, "samples": L, "sample_rate": SR,
-                   "frame": FRAME, "hop": HOP, "partitions": P, "algo": "nlms" if algo == 0 else "kalman",
-                   "l2": "inputs %.1f GB/GPU per step >> 126 MB L2 (no flush needed)" % (2 * B * L * 4 / 1e9),
-                   "parallelism": f"utterance-sharded x{world}, metrics-only all_gather",
-                   "host_cpus_rank0": (f"{len(numa_cpus)} GPU-local CPUs" if numa_cpus else "unbound")},
+        "data": "synthetic (seeded: speech-like far end, random decaying RIR, -40 dB noise)",
+        "config": workload_config(wl, world),
+        "host_cpus_rank0": (f"{len(numa_cpus)} GPU-local CPUs" if numa_cpus else "unbound"),
         "per_gpu": value / world,
-        "e2e": e2e, "e2e_bitwise_equal_to_device_path": e2e_match,
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_hbm": {"bound": "hbm", "achieved": roofline["hbm"]["achieved"], "peak": roofline["hbm"]["peak"],
                          "unit": "GB/s", "frac": roofline["hbm"]["frac"], "traffic": traffic,
                          "note": "secondary: the binding roofline of this path is FP32 (see roofline)"},
-        "cpu_baseline": cpu, "clocks": clocks,
+        "cpu_baseline": cpu, "clocks": clocks, "also": also,
         "wall_s_timed_region": wall, "erle_db_mean": erle_mean, "outputs_finite": finite,
         "parity": "FDAF recurrence: parity UNPINNED (no reference implementation); STFT/iSTFT pinned by golden vectors",
     }
