@@ -254,6 +254,105 @@ def test_pcm16_host_entry_equals_float_entry_on_quantised_input():
     assert np.array_equal(e16, ef)
 
 
+def test_host_pipeline_geometry_does_not_change_the_result():
+    """slots in flight, slice size and the start ramp are scheduling only: every geometry gives the device path's bits"""
+    B, L = 200, 4096 + 50
+    d = synth.make_batch(40, 8, L)
+    far, mic = np.tile(d["far"], (B // 8, 1)), np.tile(d["mic"], (B // 8, 1))
+    far[3] *= 0.5
+    cfg = A.Stage1Config(erle_skip_hops=2)
+    dev, dev_erle = A.stage1_aec(_cuda(far), _cuda(mic), cfg, return_erle=True)
+    dev, dev_erle = dev.cpu().numpy(), dev_erle.cpu().numpy()
+    hf, hm = A.pinned_empty((B, L)), A.pinned_empty((B, L))
+    hf[:], hm[:] = far, mic
+    assert A.is_pinned(hf) and not A.is_pinned(far)
+    for slots, sl, ramp in [(1, 16, True), (2, 32, False), (4, 16, True), (8, 8, True), (3, 64, True)]:
+        pipe = A.HostPipeline(sl, L, slots=slots, ramp=ramp)
+        err = A.pinned_empty((B, L))
+        erle = np.zeros(B, dtype=np.float32)
+        pipe.run(hf, hm, cfg, err=err, erle=erle)
+        pipe.close()
+        assert np.array_equal(err, dev) and np.array_equal(erle, dev_erle), (slots, sl, ramp)
+    with pytest.raises(A.AecError):
+        A.HostPipeline(16, L, slots=9)
+
+
+def test_runner_buffers_are_page_locked_and_pageable_inputs_are_staged():
+    """the generator's runner must not hand pageable arrays to cudaMemcpyAsync"""
+    from acoustic_echo_cancellation_b200 import wav2h5
+    B, L = 40, 3000
+    d = synth.make_batch(7, B, L)
+    run = wav2h5.default_runner(slice_utterances=16)
+    n = np.full(B, L, dtype=np.int64)
+    err, echo = run(d["far"], d["mic"], n)                       # pageable numpy in
+    assert run.buffers_pinned() and A.is_pinned(err) and A.is_pinned(echo)
+    assert set(run._in) == {"far", "mic"}                         # ... so they were staged
+    dev = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), A.Stage1Config(), return_echo=True)
+    assert np.array_equal(err, dev[0].cpu().numpy()) and np.array_equal(echo, dev[1].cpu().numpy())
+    err1 = err.copy()
+    err2, _ = run(d["far"][::-1].copy(), d["mic"][::-1].copy(), n)   # next call uses the OTHER output set
+    assert np.array_equal(err, err1) and np.array_equal(err2[::-1], err1)
+    run.close()
+
+
+def test_create_h5_train_end_to_end_on_the_gpu(tmp_path):
+    """wav files -> create_h5 (decode | stage 1 | write, default CUDA runner, NpzStore container) -> files whose
+    stage-1 datasets are the device path's output on the decoded signals"""
+    import types
+
+    from scipy.io import wavfile
+
+    from acoustic_echo_cancellation_b200 import wav2h5
+    wav_dir, h5_dir, list_dir = tmp_path / "wav", tmp_path / "h5", tmp_path / "lists"
+    for p in (wav_dir, h5_dir, list_dir):
+        p.mkdir()
+    ids = [str(i) for i in range(37)]
+    sig = {}
+    for i in ids:
+        u = synth.make_utterance(int(i), 5000 + 64 * int(i), rir_len=512)
+        for key, src in (("farend_speech", "far"), ("nearend_mic", "mic"), ("echo", "echo"), ("nearend_speech", "near")):
+            pcm = np.clip(np.rint(u[src] * 32768.0), -32768, 32767).astype(np.int16)
+            wavfile.write(str(wav_dir / wav2h5.WAV_PATTERNS[key].format(idx=i)), 16000, pcm)
+            sig[(i, key)] = pcm.astype(np.float32) / np.float32(32768)
+    args = types.SimpleNamespace(train_path=str(wav_dir), h5_path=str(h5_dir), list_path=str(list_dir), sr=16000)
+    st = {}
+    paths = wav2h5.create_h5(args, batch=8, h5=wav2h5.NpzStore(), stats=st)
+    assert len(paths) == 37 and st["pcm16_batches"] == 5 and st["float32_batches"] == 0
+    cfg = A.Stage1Config()
+    for p in paths[::6]:
+        i = p.split("tr_")[-1][:-3]
+        with np.load(p) as z:
+            for key in wav2h5.KEYS:
+                assert np.array_equal(z[key], sig[(i, key)])
+            dev = A.stage1_aec(_cuda(sig[(i, "farend_speech")][None]), _cuda(sig[(i, "nearend_mic")][None]), cfg,
+                               return_echo=True)
+            assert np.array_equal(z["stage1_error"], dev[0].cpu().numpy()[0])
+            assert np.array_equal(z["stage1_echo"], dev[1].cpu().numpy()[0])
+
+
+def test_full_batch_against_the_c_port_on_random_utterances():
+    """at the full config-2 and config-3 batch sizes, 32 randomly chosen utterances of the batch
+    against the float32 C port (fast enough for 10 s utterances) instead of relying on batch-invariance transitivity"""
+    from oracle import c_oracle as CO
+    rng = np.random.default_rng(11)
+    for (B, P, algo, L) in [(1024, 4, 0, 160000), (4096, 16, 1, 160000)]:
+        base = synth.make_batch(500, 16, L, rir_len=min(P * 256, 2048))
+        gains = (0.25 + 0.75 * rng.random(B)).astype(np.float32)
+        far = torch.from_numpy(base["far"]).cuda()[torch.arange(B, device="cuda") % 16] * torch.from_numpy(gains).cuda()[:, None]
+        mic = torch.from_numpy(base["mic"]).cuda()[torch.arange(B, device="cuda") % 16] * torch.from_numpy(gains).cuda()[:, None]
+        cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=125)
+        err, erle = A.stage1_aec(far, mic, cfg, return_erle=True)
+        pick = np.sort(rng.choice(B, size=32, replace=False))
+        hf, hm = far[pick].cpu().numpy(), mic[pick].cpu().numpy()
+        ref = CO.stage1(hf, hm, O.AecConfig(partitions=P, algo=algo), want_echo=False, erle_skip_hops=125)
+        got = err[pick].cpu().numpy()
+        n = A.out_samples(L)
+        assert np.abs(got[:, :n] - ref["err"][:, :n]).max() <= TOL_ERR, (B, P, algo)
+        assert np.abs(erle[pick].cpu().numpy() - ref["erle_db"]).max() <= TOL_ERLE
+        del far, mic, err
+        torch.cuda.empty_cache()
+
+
 def test_unsupported_combination_is_reported_not_emulated():
     d = synth.make_batch(0, 1, 4096)
     with pytest.raises(A.AecError) as ei:

@@ -49,6 +49,15 @@ def test_erb_filterbank_bit_exact(golden):
     assert np.array_equal(O.erb_filterbank(), golden["erb"])
 
 
+def test_product_erb_filterbank_bit_exact(golden):
+    """the PRODUCT's own bank (spectral.erb_filterbank, what a caller passes to aec_features), not only the
+    oracle's copy, against the array the reference's EquivalentRectangularBandwidth(...).filters holds"""
+    from acoustic_echo_cancellation_b200 import spectral
+
+    assert np.array_equal(spectral.erb_filterbank(), golden["erb"])
+    assert spectral.erb_filterbank().dtype == golden["erb"].dtype
+
+
 def test_feature_front_end(golden):
     f = O.stage2_features(golden["feat_mic"], golden["feat_ref"], golden["erb"])
     ref = golden["feat"]
