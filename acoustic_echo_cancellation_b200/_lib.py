@@ -43,6 +43,13 @@ class AecError(RuntimeError):
         super().__init__(what)
 
 
+class WavInfo(C.Structure):
+    """Mirror of ``struct aec_wav_info``."""
+
+    _fields_ = [("rate", C.c_int32), ("channels", C.c_int32), ("bits", C.c_int32), ("format", C.c_int32),
+                ("frames", C.c_int64), ("data_offset", C.c_int64)]
+
+
 class Stage2Weights(C.Structure):
     """Mirror of ``struct aec_stage2_weights`` (device pointers to Little_net's state_dict tensors)."""
 
@@ -72,6 +79,9 @@ SIGNATURES = {
     "aec_host_alloc_ex": (C.c_int, [C.POINTER(_P), _I64, _I32]),
     "aec_host_free": (C.c_int, [_P]),
     "aec_host_is_pinned": (C.c_int, [_P]),
+    "aec_wav_probe": (C.c_int, [C.c_char_p, C.POINTER(WavInfo)]),
+    "aec_wav_probe_batch": (C.c_int, [C.POINTER(C.c_char_p), _I64, C.POINTER(WavInfo), _I32]),
+    "aec_wav_read_pcm16_batch": (C.c_int, [C.POINTER(C.c_char_p), _I64, _P, _I64, _I64, _P, _I32, _I32]),
     "aec_stft": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P]),
     "aec_istft": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P]),
     "aec_features": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I32, C.c_float, C.c_float, _P]),

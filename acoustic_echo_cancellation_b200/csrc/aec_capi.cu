@@ -224,6 +224,7 @@ extern "C" const char* aec_strerror(int code) {
         case AEC_ECUDA: return "CUDA runtime error (see aec_last_cuda_error)";
         case AEC_ENODEVICE: return "no usable sm_100 CUDA device is current";
         case AEC_ENOMEM: return "out of memory";
+        case AEC_EIO: return "file could not be opened or read";
         default: return "unknown aec error";
     }
 }

@@ -85,6 +85,56 @@ def read_pcm16_into(path: str, info: WavInfo, row: np.ndarray) -> int:
     return n
 
 
+def _native():
+    """libaec_b200.so's batched reader (``aec_wav_probe_batch`` / ``aec_wav_read_pcm16_batch``), or None when the
+    library has not been built (host-only unit tests of this module then use the Python reader above)."""
+    try:
+        from . import _lib
+
+        return _lib, _lib.load()
+    except (ImportError, OSError, AttributeError):
+        return None
+
+
+def _c_paths(paths: Sequence[str]):
+    import ctypes as C
+
+    arr = (C.c_char_p * len(paths))()
+    arr[:] = [os.fsencode(p) for p in paths]
+    return arr
+
+
+def probe_batch(paths: Sequence[str], threads: int) -> Optional[List[WavInfo]]:
+    """Headers of many files at once through the native reader; None if it is unavailable."""
+    nat = _native()
+    if nat is None or not paths:
+        return None if nat is None else []
+    _lib, lib = nat
+    infos = (_lib.WavInfo * len(paths))()
+    rc = lib.aec_wav_probe_batch(_c_paths(paths), len(paths), infos, int(threads))
+    if rc == -6:
+        raise IOError("aec_wav_probe_batch: a wav file could not be opened or read")
+    if rc != 0:
+        raise ValueError("aec_wav_probe_batch: not a RIFF/WAVE file")
+    return [WavInfo(i.rate, i.channels, i.bits, i.format, i.frames, i.data_offset) for i in infos]
+
+
+def read_pcm16_batch(paths: Sequence[str], dst: np.ndarray, sr: int, threads: int) -> Optional[np.ndarray]:
+    """Native multi-threaded read of fast-path files into the rows of ``dst`` ([n, cols] int16, contiguous rows).
+    Returns the true frame counts, or None when a file is not 16-bit mono PCM at ``sr`` (caller falls back)."""
+    _lib, lib = _native()
+    n = len(paths)
+    frames = np.zeros(n, dtype=np.int64)
+    assert dst.dtype == np.int16 and dst.strides[1] == 2 and dst.shape[0] >= n
+    rc = lib.aec_wav_read_pcm16_batch(_c_paths(paths), n, dst.ctypes.data, dst.strides[0] // 2, dst.shape[1],
+                                      frames.ctypes.data, int(sr), int(threads))
+    if rc == -2:
+        return None
+    if rc != 0:
+        raise IOError(f"aec_wav_read_pcm16_batch failed ({rc})")
+    return frames
+
+
 def load_wav(path: str, sr: int) -> np.ndarray:
     """mono float32 at ``sr`` (what ``librosa.load(path, sr=sr)`` returns, train_wav2h5.py:20)."""
     try:
@@ -138,8 +188,11 @@ class BatchDecoder:
     in host-only tests).  ``sets`` buffer sets are cycled, so that a batch can still be on the GPU / being
     written while the next ones are decoded."""
 
-    def __init__(self, sr: int, threads: int = 8, alloc: Optional[Callable] = None, sets: int = 3):
+    def __init__(self, sr: int, threads: int = 8, alloc: Optional[Callable] = None, sets: int = 3,
+                 native: Optional[bool] = None):
         self.sr = int(sr)
+        self.threads = max(1, int(threads))
+        self.native = (_native() is not None) if native is None else bool(native)
         self.pool = ThreadPoolExecutor(max(1, int(threads)), thread_name_prefix="aec-wav")
         self.alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype=dtype))
         self.sets = [dict() for _ in range(max(1, sets))]
@@ -149,13 +202,15 @@ class BatchDecoder:
         self.pool.shutdown(wait=True)
         self.sets = []
 
-    def _buffer(self, slot: dict, name: str, nb: int, lmax: int, dtype) -> np.ndarray:
+    def _buffer(self, slot: dict, name: str, nb: int, lmax: int, dtype, upload: bool = True) -> np.ndarray:
+        """[nb, lmax] view of a reusable batch buffer of this set; ``upload=False``: stored-only signals, plain
+        (pageable) memory is enough."""
         key = (name, np.dtype(dtype).str)
         buf = slot.get(key)
         if buf is None or buf.shape[0] < nb or buf.shape[1] < lmax:
             rows = max(nb, buf.shape[0] if buf is not None else 0)
             cols = max(lmax, buf.shape[1] if buf is not None else 0)
-            buf = self.alloc((rows, cols), dtype)
+            buf = self.alloc((rows, cols), dtype) if upload else np.empty((rows, cols), dtype=dtype)
             slot[key] = buf
         # [nb, lmax] view with the buffer's row pitch would not be contiguous; the host entry takes a stride
         return buf[:nb, :lmax]
@@ -167,6 +222,10 @@ class BatchDecoder:
         nb = len(far_paths)
         slot = self.sets[self._next]
         self._next = (self._next + 1) % len(self.sets)
+        if self.native:
+            b = self._decode_native(slot, far_paths, mic_paths, extra)
+            if b is not None:
+                return b
         infos = list(self.pool.map(probe_wav, list(far_paths) + list(mic_paths)))
         fi, mi = infos[:nb], infos[nb:]
         fast = all(a.fast(self.sr) for a in infos)
@@ -223,6 +282,47 @@ class BatchDecoder:
         for key, paths in extra.items():
             signals[key] = list(self.pool.map(stored, paths))
         return DecodedBatch(far=far, mic=mic, n=n, pcm16=fast, signals=signals)
+
+
+def _decode_native(self, slot, far_paths, mic_paths, extra) -> Optional[DecodedBatch]:
+    """All-native form of the fast path: one probe call, one read call per signal (C++ threads, no GIL)."""
+    nb = len(far_paths)
+    infos = probe_batch(list(far_paths) + list(mic_paths), self.threads)
+    if not all(a.fast(self.sr) for a in infos):
+        return None
+    fi, mi = infos[:nb], infos[nb:]
+    n = np.array([a.frames for a in fi], dtype=np.int64)
+    lmax = int(max(int(n.max()), 1))
+    far = self._buffer(slot, "far", nb, lmax, np.int16)
+    mic = self._buffer(slot, "mic", nb, lmax, np.int16)
+    if read_pcm16_batch(far_paths, far, self.sr, self.threads) is None:
+        return None
+    if read_pcm16_batch(mic_paths, mic, self.sr, self.threads) is None:
+        return None
+    signals: Dict[str, List[np.ndarray]] = {"__far__": [far[j, :n[j]] for j in range(nb)], "__mic__": []}
+    for j in range(nb):
+        if mi[j].frames > n[j]:
+            mic[j, n[j]:] = 0                       # the uploaded row follows the far-end clock
+        signals["__mic__"].append(mic[j, :n[j]] if mi[j].frames == n[j] else None)
+    ragged = [j for j in range(nb) if signals["__mic__"][j] is None]
+    for key, paths in list(extra.items()) + ([("__mic__", [mic_paths[j] for j in ragged])] if ragged else []):
+        ki = probe_batch(paths, self.threads)
+        if not all(a.fast(self.sr) for a in ki):
+            out = list(self.pool.map(lambda p: load_wav(p, self.sr), paths))
+        else:
+            cols = int(max([a.frames for a in ki] + [1]))
+            buf = self._buffer(slot, "store_" + key, len(paths), cols, np.int16, upload=False)
+            fr = read_pcm16_batch(paths, buf, self.sr, self.threads)
+            out = [buf[j, :fr[j]] for j in range(len(paths))]
+        if key == "__mic__":
+            for j, a in zip(ragged, out):
+                signals["__mic__"][j] = a
+        else:
+            signals[key] = out
+    return DecodedBatch(far=far, mic=mic, n=n, pcm16=True, signals=signals)
+
+
+BatchDecoder._decode_native = _decode_native
 
 
 def as_float32(a: np.ndarray) -> np.ndarray:

@@ -211,6 +211,61 @@ class _NpzFile(_NpzGroup):
         self._members = {}
 
 
+class _RawGroup:
+    def __init__(self, root: "_RawFile", prefix: str):
+        self._root, self._prefix = root, prefix
+
+    def create_dataset(self, name, data=None, shape=None, chunks=None):
+        a = np.ascontiguousarray(data)
+        f = self._root._f
+        self._root._index.append((self._prefix + name, a.dtype.str, list(a.shape), f.tell()))
+        f.write(memoryview(a).cast("B"))                  # (the write releases the GIL)
+
+    def create_group(self, name):
+        return _RawGroup(self._root, self._prefix + str(name) + "/")
+
+
+class _RawFile(_RawGroup):
+    def __init__(self, path: str):
+        super().__init__(self, "")
+        self._f = open(path, "wb", buffering=0)
+        self._f.write(b"AECRAW01" + b"\0" * 8)            # magic + offset of the index (patched on close)
+        self._index = []
+
+    def close(self):
+        import json
+
+        pos = self._f.tell()
+        self._f.write(json.dumps(self._index).encode())
+        self._f.seek(8)
+        self._f.write(int(pos).to_bytes(8, "little"))
+        self._f.close()
+
+
+class RawStore:
+    """Second stand-in container for boxes without h5py, built for speed: the datasets' bytes one after the other
+    plus a JSON index at the end (``RawStore.load(path)`` reads it back).  What the file-pipeline measurement
+    (tools/config5_files.py) writes; like ``NpzStore`` it is NOT readable by the reference's readers."""
+
+    def File(self, name, mode):
+        assert mode == "w"
+        return _RawFile(name)
+
+    @staticmethod
+    def load(path: str) -> Dict[str, np.ndarray]:
+        import json
+
+        with open(path, "rb") as f:
+            blob = f.read()
+        assert blob[:8] == b"AECRAW01"
+        pos = int.from_bytes(blob[8:16], "little")
+        out = {}
+        for name, dt, shape, off in json.loads(blob[pos:].decode()):
+            n = int(np.prod(shape)) if shape else 1
+            out[name] = np.frombuffer(blob, dtype=np.dtype(dt), count=n, offset=off).reshape(shape)
+        return out
+
+
 class NpzStore:
     """Stand-in container with the slice of the ``h5py`` surface the generators use, for boxes without h5py:
     one uncompressed npz (zip of .npy) per ``File``, member names ``<group>/<dataset>``."""

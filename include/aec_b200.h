@@ -39,7 +39,8 @@ enum {
     AEC_EUNSUPPORTED = -2, /* frame / partitions / algo combination not built */
     AEC_ECUDA = -3,       /* a CUDA runtime call failed; see aec_last_cuda_error() */
     AEC_ENODEVICE = -4,   /* no sm_100 device is current */
-    AEC_ENOMEM = -5
+    AEC_ENOMEM = -5,
+    AEC_EIO = -6          /* a file could not be opened / read (wav ingest) */
 };
 
 enum { AEC_ALGO_NLMS = 0, AEC_ALGO_KALMAN = 1 };
@@ -134,6 +135,26 @@ int aec_host_alloc_ex(void** ptr, int64_t bytes, int32_t flags);
 int aec_host_free(void* ptr);
 /* 1 if ptr lies in page-locked host memory known to CUDA, 0 if not (pageable / unknown) */
 int aec_host_is_pinned(const void* ptr);
+
+/* Batched wav ingest (host code): what replaces the four serial `librosa.load(path, sr=args.sr)` calls per
+ * utterance of the generators (Stage2_lhm/generate_h5files/train_wav2h5.py:20-23, test_wav2h5.py:29-32,
+ * val_wav2h5.py:33-36) for the format those corpora are in -- 16-bit PCM, mono, already at the target rate.
+ * aec_wav_probe parses the RIFF chunk list (no samples read).  aec_wav_read_pcm16_batch reads n files with
+ * `threads` threads into rows of an int16 batch buffer (row i at dst + i * row_stride; the first
+ * min(frames, row_samples) samples, zero-filled up to row_samples), storing the true frame counts in frames[]
+ * (nullable).  Files that are not 16-bit mono PCM at expect_rate (expect_rate <= 0: any rate) make the call return
+ * AEC_EUNSUPPORTED -- the caller decodes that batch with a general loader; the samples are never touched here
+ * (int16 in, int16 out; `x / 32768`, librosa's scaling, is applied on the GPU by aec_stage1_run_host_pcm16). */
+typedef struct aec_wav_info {
+    int32_t rate, channels, bits;
+    int32_t format;      /* 1 = integer PCM, 3 = IEEE float (WAVE_FORMAT_EXTENSIBLE resolved to its sub-format) */
+    int64_t frames;      /* samples per channel in the data chunk */
+    int64_t data_offset; /* byte offset of the first sample */
+} aec_wav_info;
+int aec_wav_probe(const char* path, aec_wav_info* info);
+int aec_wav_probe_batch(const char* const* paths, int64_t n, aec_wav_info* infos, int32_t threads);
+int aec_wav_read_pcm16_batch(const char* const* paths, int64_t n, int16_t* dst, int64_t row_stride,
+                             int64_t row_samples, int64_t* frames, int32_t expect_rate, int32_t threads);
 
 /* STFT analysis on DEVICE buffers: replaces ConvSTFT(frame, frame/2, frame, 'hann', 'complex')
  * .forward (Stage2_lhm/scripts/network/attention_ccrn.py:45-52).

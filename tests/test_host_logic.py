@@ -198,6 +198,14 @@ def test_create_h5_float_wavs_take_the_float32_path_and_npz_store_round_trips(tm
             assert set(z.files) == set(wav2h5.KEYS) | {"stage1_error", "stage1_echo"}
             assert np.array_equal(z["farend_speech"], data[(idx, "farend_speech")])
             assert np.array_equal(z["stage1_error"], np.float32(0.5) * z["farend_speech"])
+    args.val_path, args.train_path = args.train_path, None
+    path = wav2h5.create_h5(args, runner=_fake_runner, batch=1, h5=wav2h5.RawStore())     # test form, raw container
+    z = wav2h5.RawStore.load(path)
+    names = open(list_dir / "filename.txt").read().split("\n")
+    assert sorted(z) == sorted(f"{g}/{k}" for g in range(2) for k in wav2h5.KEYS + ("stage1_error", "stage1_echo"))
+    for g, idx in enumerate(names):
+        assert np.array_equal(z[f"{g}/echo"], data[(idx, "echo")])
+        assert np.array_equal(z[f"{g}/stage1_echo"], np.float32(0.25) * z[f"{g}/nearend_mic"])
 
 
 def test_wav_probe_and_pcm16_fast_read(tmp_path):
@@ -233,6 +241,24 @@ def test_wav_probe_and_pcm16_fast_read(tmp_path):
     assert np.array_equal(b.mic[1], x)
     assert len(b.signals["__mic__"][0]) == 1000 and len(b.signals["__mic__"][1]) == 1284
     dec.close()
+    # the native reader of libaec_b200.so (C++ threads) and the Python reader give the same batch
+    assert dec.native, "libaec_b200.so must be built for the CPU suite (make -C .../csrc)"
+    py = ingest.BatchDecoder(16000, threads=2, native=False)
+    c = py.decode([far, far], [mic_short, mic_long], {"echo": [far, far]})
+    assert c.pcm16 and np.array_equal(c.far, b.far) and np.array_equal(c.mic, b.mic) and np.array_equal(c.n, b.n)
+    for key in ("__far__", "__mic__", "echo"):
+        assert all(np.array_equal(x, y) for x, y in zip(b.signals[key], c.signals[key])), key
+    py.close()
+    infos = ingest.probe_batch([far, mic_short], 2)
+    assert [(i.rate, i.channels, i.bits, i.fmt, i.frames) for i in infos] == [(16000, 1, 16, 1, 1234), (16000, 1, 16, 1, 1000)]
+    assert ingest.probe_batch([far], 1)[0] == ingest.probe_wav(far)
+    with pytest.raises(ValueError):
+        ingest.probe_batch([str(tmp_path / "bad.wav")], 1)
+    with pytest.raises(IOError):
+        ingest.probe_batch([str(tmp_path / "missing.wav")], 1)
+    dst = np.full((1, 1500), 9, dtype=np.int16)
+    wavfile.write(p, 8000, x)                                    # wrong rate -> not the fast path
+    assert ingest.read_pcm16_batch([p], dst, 16000, 1) is None
 
 
 def _shard_worker(rank, world, port, folder, ret):

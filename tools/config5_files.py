@@ -12,8 +12,8 @@ What is and is not measured
   which no box here holds; the per-utterance work is the same and throughput is reported per utterance.
 * Files go to --root (default /dev/shm when it has room, else the system temp dir): the page cache / tmpfs, not a
   disk array -- this measures the pipeline (decode, PCIe, kernel, container write), not a storage system.
-* h5py is absent from the image: the container is wav2h5.NpzStore (uncompressed .npz per utterance, same keys) unless
-  h5py imports; the JSON line says which.
+* h5py is absent from the image: the container is wav2h5.RawStore (the datasets' bytes + an index per utterance,
+  same keys) unless h5py imports; the JSON line says which.
 * `reference_loop`: the reference's loop shape on ONE core (its scripts are single-threaded) over a bounded sample --
   scipy decode x 4 + one container write per utterance, without any filter (the reference has none) and, second
   figure, with the single-threaded C port of the stage-1 filter in the loop.
@@ -125,14 +125,15 @@ def main():
         import h5py  # type: ignore
         store, container = h5py, "h5py"
     except ImportError:
-        store, container = wav2h5.NpzStore(), "NpzStore (.npz stand-in: h5py is not installed)"
+        store, container = wav2h5.RawStore(), "RawStore (raw stand-in container: h5py is not installed)"
     ns = types.SimpleNamespace(train_path=train_dir, h5_path=h5_dir, list_path=list_dir, sr=sr)
     runner = wav2h5.default_runner(slice_utterances=128, device=local)
     # warm-up: CUDA context, page-locked buffers, kernel load (a small separate run into a scratch folder)
     warm = types.SimpleNamespace(train_path=os.path.join(work, f"warm{rank}"), h5_path=os.path.join(work, f"warm_h5_{rank}"),
                                  list_path=os.path.join(work, f"warm_l_{rank}"), sr=sr)
     os.makedirs(warm.list_path, exist_ok=True)
-    link_ids(pool_dir, warm.train_path, args.pool, 10 ** 9 + rank * 1000, min(args.batch, 64))
+    # (as many utterances as every rank's shard of them is one full batch: the page-locked buffers get their final size)
+    link_ids(pool_dir, warm.train_path, args.pool, 10 ** 9 + rank * 100000, args.batch * world)
     wav2h5.create_h5_train(warm, runner=runner, batch=args.batch, h5=store, decode_threads=dthreads,
                            write_threads=wthreads, pinned=True)
     if world > 1:
