@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(kThreads) features512_kernel(const float* __re
                                                                const float* __restrict__ ref,
                                                                const float* __restrict__ erb, float* __restrict__ feat,
                                                                long long L, long long in_stride, long long T, int bands,
-                                                               float shift_mic, float shift_ref, Tables tab) {
+                                                               float shift_mic, float shift_ref,
+                                                               const float* __restrict__ shift_mic_dev,
+                                                               const float* __restrict__ shift_ref_dev, Tables tab) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tiles = reinterpret_cast<float2*>(smem);                                  // [8][kTilePitch]
     float* mag = reinterpret_cast<float*>(smem + 8 * kTilePitch * sizeof(float2));    // [2][kTT][kFeatMP]
@@ -231,7 +233,9 @@ __global__ void __launch_bounds__(kThreads) features512_kernel(const float* __re
         }
     }
     const float* xb = (half == 0 ? mic : ref) + b * in_stride;
-    const float shift = half == 0 ? shift_mic : shift_ref;
+    // the batch-global scalar of ERB.py:254-255, by value or -- no host round trip -- from aec_batch_shift's output
+    const float shift = half == 0 ? (shift_mic_dev ? __ldg(shift_mic_dev) : shift_mic)
+                                  : (shift_ref_dev ? __ldg(shift_ref_dev) : shift_ref);
     float2* tile = tiles + (2 * warp + half) * kTilePitch;
     float* fb = feat + b * T * (2 * bands);
 
@@ -520,9 +524,97 @@ extern "C" int aec_istft(const float* spec, float* y, int64_t B, int64_t T, int6
     return AEC_OK;
 }
 
-extern "C" int aec_features(const float* mic, const float* ref, const float* erb, float* feat, int64_t B, int64_t L,
-                            int64_t in_stride, int32_t frame, int32_t bands, float shift_mic, float shift_ref,
-                            void* cuda_stream) {
+namespace aec {
+namespace {
+// ---------------------------------------------------------------------------------------
+// Batch-global shift mean(x) / std(x) (unbiased, torch.std) of ERB.py:254-256, on the device: per-CTA partial sums
+// in double (fixed order -> deterministic), one finishing CTA; the scalar stays in device memory.
+// ---------------------------------------------------------------------------------------
+constexpr int kShiftCtas = 592, kShiftThreads = 256;
+
+__global__ void __launch_bounds__(kShiftThreads) shift_partial_kernel(const float* __restrict__ x, long long B, long long L,
+                                                                      long long stride, double* __restrict__ part) {
+    double s = 0.0, q = 0.0;
+    const bool vec = (L % 4 == 0) && (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (vec) {
+        const long long per_row = L / 4, total = B * per_row;
+        for (long long i = (long long)blockIdx.x * kShiftThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kShiftThreads) {
+            const long long r = i / per_row, c = i - r * per_row;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * stride) + c);
+            const float a = (v.x + v.y) + (v.z + v.w);
+            const float b2 = fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+            s += (double)a;
+            q += (double)b2;
+        }
+    } else {
+        const long long total = B * L;
+        for (long long i = (long long)blockIdx.x * kShiftThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kShiftThreads) {
+            const long long r = i / L, c = i - r * L;
+            const float v = __ldg(x + r * stride + c);
+            s += (double)v;
+            q += (double)v * (double)v;
+        }
+    }
+    __shared__ double sh[2][kShiftThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = s;
+        sh[1][threadIdx.x >> 5] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tq = 0.0;
+        for (int w = 0; w < kShiftThreads / 32; ++w) {
+            ts += sh[0][w];
+            tq += sh[1][w];
+        }
+        part[2 * blockIdx.x] = ts;
+        part[2 * blockIdx.x + 1] = tq;
+    }
+}
+
+__global__ void __launch_bounds__(32) shift_finish_kernel(const double* __restrict__ part, int n_part, double count,
+                                                          float* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < n_part; ++i) {
+        s += part[2 * i];
+        q += part[2 * i + 1];
+    }
+    const double mean = s / count;
+    const double var = count > 1.0 ? (q - s * mean) / (count - 1.0) : 0.0;       // unbiased, like torch.std
+    out[0] = (float)(mean / sqrt(var > 0.0 ? var : 0.0));                          // (std = 0 -> inf / nan, as in torch)
+}
+
+}  // namespace
+}  // namespace aec
+
+using namespace aec;
+
+extern "C" int64_t aec_batch_shift_workspace_bytes(void) { return (int64_t)kShiftCtas * 2 * sizeof(double); }
+
+extern "C" int aec_batch_shift(const float* x, int64_t B, int64_t L, int64_t stride, float* shift_dev, void* workspace,
+                               int64_t workspace_bytes, void* cuda_stream) {
+    if (B <= 0 || L <= 0 || stride < L || !x || !shift_dev || !workspace) return AEC_EINVAL;
+    if (workspace_bytes < aec_batch_shift_workspace_bytes() || (reinterpret_cast<uintptr_t>(workspace) & 7)) return AEC_EINVAL;
+    Tables tab;
+    const int rc = get_tables(&tab);                  // device check (sm_100 only)
+    if (rc != AEC_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    shift_partial_kernel<<<kShiftCtas, kShiftThreads, 0, s>>>(x, B, L, stride, static_cast<double*>(workspace));
+    shift_finish_kernel<<<1, 32, 0, s>>>(static_cast<const double*>(workspace), kShiftCtas, (double)B * (double)L, shift_dev);
+    AEC_CUDA_CHECK(cudaGetLastError());
+    count_launch(2);
+    return AEC_OK;
+}
+
+static int features_impl(const float* mic, const float* ref, const float* erb, float* feat, int64_t B, int64_t L,
+                         int64_t in_stride, int32_t frame, int32_t bands, float shift_mic, float shift_ref,
+                         const float* shift_mic_dev, const float* shift_ref_dev, void* cuda_stream) {
     if (B < 0 || L < 0 || in_stride < L || bands < 1 || bands > 64) return AEC_EINVAL;
     if (frame != 512) return frame == 1024 ? AEC_EUNSUPPORTED : AEC_EINVAL;
     if (B == 0) return AEC_OK;
@@ -530,9 +622,9 @@ extern "C" int aec_features(const float* mic, const float* ref, const float* erb
     if (B > kMaxGridY) {
         const long long per = 2LL * bands * aec_num_frames(L, frame);
         for (int64_t off = 0; off < B; off += kMaxGridY) {
-            const int rc2 = aec_features(mic + off * in_stride, ref + off * in_stride, erb, feat + off * per,
-                                         (B - off < kMaxGridY) ? B - off : kMaxGridY, L, in_stride, frame, bands,
-                                         shift_mic, shift_ref, cuda_stream);
+            const int rc2 = features_impl(mic + off * in_stride, ref + off * in_stride, erb, feat + off * per,
+                                          (B - off < kMaxGridY) ? B - off : kMaxGridY, L, in_stride, frame, bands,
+                                          shift_mic, shift_ref, shift_mic_dev, shift_ref_dev, cuda_stream);
             if (rc2 != AEC_OK) return rc2;
         }
         return AEC_OK;
@@ -554,8 +646,22 @@ extern "C" int aec_features(const float* mic, const float* ref, const float* erb
     if (per_utt < 1) per_utt = 1;
     dim3 grid((unsigned)per_utt, (unsigned)B);
     features512_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
-        mic, ref, erb, feat, L, in_stride, T, bands, shift_mic, shift_ref, tab);
+        mic, ref, erb, feat, L, in_stride, T, bands, shift_mic, shift_ref, shift_mic_dev, shift_ref_dev, tab);
     AEC_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return AEC_OK;
+}
+
+extern "C" int aec_features(const float* mic, const float* ref, const float* erb, float* feat, int64_t B, int64_t L,
+                            int64_t in_stride, int32_t frame, int32_t bands, float shift_mic, float shift_ref,
+                            void* cuda_stream) {
+    return features_impl(mic, ref, erb, feat, B, L, in_stride, frame, bands, shift_mic, shift_ref, nullptr, nullptr,
+                         cuda_stream);
+}
+
+extern "C" int aec_features_dev(const float* mic, const float* ref, const float* erb, float* feat, int64_t B, int64_t L,
+                                int64_t in_stride, int32_t frame, int32_t bands, const float* shift_mic_dev,
+                                const float* shift_ref_dev, void* cuda_stream) {
+    return features_impl(mic, ref, erb, feat, B, L, in_stride, frame, bands, 0.f, 0.f, shift_mic_dev, shift_ref_dev,
+                         cuda_stream);
 }

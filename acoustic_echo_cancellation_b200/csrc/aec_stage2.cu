@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(kThreads) stage2_synth_kernel(const float* __r
                                                                 const float* __restrict__ est,
                                                                 const float* __restrict__ erb, float* __restrict__ y,
                                                                 long long L, long long in_stride, long long out_stride,
-                                                                long long T, float shift, Tables tab) {
+                                                                long long T, float shift_val,
+                                                                const float* __restrict__ shift_dev, Tables tab) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tiles = reinterpret_cast<float2*>(smem);                                   // [8][kTilePitch]
     float2* fr = tiles + 8 * kTilePitch;                                               // [kTT][256]
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(kThreads) stage2_synth_kernel(const float* __r
     int* bhi = blo + kK;                                                               // [257]
     const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
     const long long b = blockIdx.y, g0 = (long long)blockIdx.x * (kTT - 1);
+    const float shift = shift_dev ? __ldg(shift_dev) : shift_val;      // ERB.py:254, by value or from aec_batch_shift
     for (int i = tid; i < kK * kH; i += kThreads) erbs[i] = __ldg(erb + i);
     for (int i = tid; i < kTT * kH; i += kThreads) {
         const long long t = g0 + i / kH;
@@ -301,9 +303,9 @@ extern "C" int aec_stage2_mask(const float* feat, const aec_stage2_weights* w, f
     return AEC_OK;
 }
 
-extern "C" int aec_stage2_synth(const float* mic, const float* est_erb, const float* erb, float* out, int64_t B,
-                                int64_t L, int64_t in_stride, int64_t out_stride, int32_t frame, int32_t bands,
-                                float shift_mic, void* cuda_stream) {
+static int synth_impl(const float* mic, const float* est_erb, const float* erb, float* out, int64_t B, int64_t L,
+                      int64_t in_stride, int64_t out_stride, int32_t frame, int32_t bands, float shift_mic,
+                      const float* shift_mic_dev, void* cuda_stream) {
     if (B < 0 || L < 0 || in_stride < L) return AEC_EINVAL;
     if (frame != 512 || bands != kH) return AEC_EUNSUPPORTED;
     const long long T = aec_num_frames(L, frame);
@@ -312,9 +314,9 @@ extern "C" int aec_stage2_synth(const float* mic, const float* est_erb, const fl
     if (!mic || !est_erb || !erb || !out) return AEC_EINVAL;
     if (B > 65535) {            // grid.y carries the utterance index: larger batches go in slices
         for (int64_t off = 0; off < B; off += 65535) {
-            const int rc2 = aec_stage2_synth(mic + off * in_stride, est_erb + off * T * kH, erb, out + off * out_stride,
-                                             (B - off < 65535) ? B - off : 65535, L, in_stride, out_stride, frame, bands,
-                                             shift_mic, cuda_stream);
+            const int rc2 = synth_impl(mic + off * in_stride, est_erb + off * T * kH, erb, out + off * out_stride,
+                                       (B - off < 65535) ? B - off : 65535, L, in_stride, out_stride, frame, bands,
+                                       shift_mic, shift_mic_dev, cuda_stream);
             if (rc2 != AEC_OK) return rc2;
         }
         return AEC_OK;
@@ -327,8 +329,20 @@ extern "C" int aec_stage2_synth(const float* mic, const float* est_erb, const fl
     AEC_CUDA_CHECK(cudaFuncSetAttribute(stage2_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((T - 1 + kTT - 2) / (kTT - 1)), (unsigned)B);
     stage2_synth_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
-        mic, est_erb, erb, out, L, in_stride, out_stride, T, shift_mic, tab);
+        mic, est_erb, erb, out, L, in_stride, out_stride, T, shift_mic, shift_mic_dev, tab);
     AEC_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return AEC_OK;
+}
+
+extern "C" int aec_stage2_synth(const float* mic, const float* est_erb, const float* erb, float* out, int64_t B,
+                                int64_t L, int64_t in_stride, int64_t out_stride, int32_t frame, int32_t bands,
+                                float shift_mic, void* cuda_stream) {
+    return synth_impl(mic, est_erb, erb, out, B, L, in_stride, out_stride, frame, bands, shift_mic, nullptr, cuda_stream);
+}
+
+extern "C" int aec_stage2_synth_dev(const float* mic, const float* est_erb, const float* erb, float* out, int64_t B,
+                                    int64_t L, int64_t in_stride, int64_t out_stride, int32_t frame, int32_t bands,
+                                    const float* shift_mic_dev, void* cuda_stream) {
+    return synth_impl(mic, est_erb, erb, out, B, L, in_stride, out_stride, frame, bands, 0.f, shift_mic_dev, cuda_stream);
 }

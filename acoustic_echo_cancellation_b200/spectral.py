@@ -3,6 +3,7 @@
     ConvSTFT   <-> Stage2_lhm/scripts/network/attention_ccrn.py:28-59
     ConviSTFT  <-> Stage2_lhm/scripts/network/attention_ccrn.py:62-101
     stage2_features <-> Stage2_lhm/scripts/network/ERB.py:254-290
+    batch_shift     <-> the scalar mean/std of ERB.py:254-256 (device-side reduction, no host sync)
     erb_filterbank  <-> Stage2_lhm/scripts/network/ERB.py:10-71 (host-side table, numpy)
 
 Same constructor arguments, same tensor layouts ([B, 2K, T] real-over-imag; [B, 1, L']),
@@ -110,8 +111,27 @@ def erb_filterbank(nfreqs=257, sample_rate=16000, total_erb_bands=32, low_freq=0
     return bank
 
 
+def batch_shift(x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """The scalar ``x.mean() / x.std()`` over the WHOLE batch tensor that ERB.py:254-256 subtracts, computed by
+    ``aec_batch_shift`` and left on the device (a 1-element float32 CUDA tensor): no host synchronisation."""
+    _require_cuda_f32("x", x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be [B, L] with unit inner stride")
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        if out is None:
+            out = torch.empty(1, dtype=torch.float32, device=x.device)
+        nbytes = int(lib.aec_batch_shift_workspace_bytes())
+        ws = torch.empty(nbytes // 8, dtype=torch.float64, device=x.device)
+        B, L = x.shape
+        rc = lib.aec_batch_shift(x.data_ptr(), B, L, max(x.stride(0), L) if B > 1 else L, out.data_ptr(), ws.data_ptr(),
+                                 nbytes, _stream_ptr(x))
+    _lib.check(rc, "aec_batch_shift")
+    return out
+
+
 def stage2_features(mic: torch.Tensor, ref: torch.Tensor, erb: torch.Tensor, frame: int = 512,
-                    in_norm: bool = True) -> torch.Tensor:
+                    in_norm: bool = True, shifts=None) -> torch.Tensor:
     """Feature tensor fed to the Stage-2 GRU: ``cat[mic_erb, |mic_erb - ref_erb|]`` [B, T, 2*bands]
     (ERB.py:254-290) in ONE kernel: no [B, 514, T] spectra are materialised.  ``mic`` would be the
     stage-1 error signal in a two-stage pipeline; ``erb`` is [257, bands] float32 on the device."""
@@ -126,13 +146,19 @@ def stage2_features(mic: torch.Tensor, ref: torch.Tensor, erb: torch.Tensor, fra
     if erb.shape[0] != K:
         raise ValueError(f"erb must be [{K}, bands]")
     bands = erb.shape[1]
-    # ERB.py:254-255 subtract the batch-global scalar mean/std (torch.std is unbiased)
-    sm = float(mic.mean() / mic.std()) if in_norm else 0.0
-    sr = float(ref.mean() / ref.std()) if in_norm else 0.0
+    # ERB.py:254-255 subtract the batch-global scalar mean/std (torch.std is unbiased): reduced on the device and
+    # handed to the feature kernel by device pointer -- the call stays asynchronous (``shifts`` = precomputed pair)
+    if shifts is not None:
+        sm, sr = shifts
+    elif in_norm:
+        sm, sr = batch_shift(mic), batch_shift(ref)
+    else:
+        sm = sr = None
     T = num_frames(L, frame)
     with torch.cuda.device(mic.device):
         feat = torch.empty((B, T, 2 * bands), dtype=torch.float32, device=mic.device)
-        rc = _lib.load().aec_features(mic.data_ptr(), ref.data_ptr(), erb.data_ptr(), feat.data_ptr(), B, L, L,
-                                      frame, bands, sm, sr, _stream_ptr(mic))
-    _lib.check(rc, "aec_features")
+        rc = _lib.load().aec_features_dev(mic.data_ptr(), ref.data_ptr(), erb.data_ptr(), feat.data_ptr(), B, L, L,
+                                          frame, bands, sm.data_ptr() if sm is not None else None,
+                                          sr.data_ptr() if sr is not None else None, _stream_ptr(mic))
+    _lib.check(rc, "aec_features_dev")
     return feat

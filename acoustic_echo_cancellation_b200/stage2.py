@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .spectral import stage2_features
+from .spectral import batch_shift, stage2_features
 from .stage1 import _require_cuda_f32, _stream_ptr, num_frames, out_samples
 
 _KEYS = {
@@ -60,9 +60,12 @@ class LittleNetInference:
         mic, ref = mic.contiguous(), ref.contiguous()
         B, L = mic.shape
         lib = _lib.load()
-        # ERB.py:254: the batch-global scalar mean/std is subtracted (torch.std is unbiased)
-        shift_mic = float(mic.mean() / mic.std()) if in_norm else 0.0
-        feat = stage2_features(mic, ref, self.erb, in_norm=in_norm)              # [B, T, 64]
+        # ERB.py:254: the batch-global scalar mean/std is subtracted (torch.std is unbiased); reduced on the device
+        # once per signal and passed by device pointer -- the whole forward is asynchronous, no host round trip
+        shift_mic = batch_shift(mic) if in_norm else None
+        shift_ref = batch_shift(ref) if in_norm else None
+        feat = stage2_features(mic, ref, self.erb, in_norm=in_norm,
+                               shifts=(shift_mic, shift_ref) if in_norm else None)   # [B, T, 64]
         T = num_frames(L)
         with torch.cuda.device(mic.device):
             est = torch.empty((B, T, 32), dtype=torch.float32, device=mic.device)
@@ -71,6 +74,8 @@ class LittleNetInference:
             _lib.check(lib.aec_stage2_mask(feat.data_ptr(), C.byref(self._cw), est.data_ptr(), B, T, 32, s),
                        "aec_stage2_mask")
             if out.numel():
-                _lib.check(lib.aec_stage2_synth(mic.data_ptr(), est.data_ptr(), self.erb.data_ptr(), out.data_ptr(),
-                                                B, L, L, out.shape[1], 512, 32, shift_mic, s), "aec_stage2_synth")
+                _lib.check(lib.aec_stage2_synth_dev(mic.data_ptr(), est.data_ptr(), self.erb.data_ptr(), out.data_ptr(),
+                                                    B, L, L, out.shape[1], 512, 32,
+                                                    shift_mic.data_ptr() if shift_mic is not None else None, s),
+                           "aec_stage2_synth_dev")
         return out

@@ -177,6 +177,18 @@ int aec_features(const float* mic, const float* ref, const float* erb, float* fe
                  int64_t in_stride, int32_t frame, int32_t bands, float shift_mic, float shift_ref,
                  void* cuda_stream);
 
+/* The batch-global scalar of ERB.py:254-256, mean(x) / std(x) over ALL B*L samples (unbiased std, torch.std),
+ * computed on the device and left there: shift_dev[0] feeds aec_features_dev / aec_stage2_synth_dev without a host
+ * round trip.  `workspace`: caller-owned device memory of at least aec_batch_shift_workspace_bytes() bytes (8-byte
+ * aligned); partial sums are accumulated in double in a fixed order (deterministic). */
+int64_t aec_batch_shift_workspace_bytes(void);
+int aec_batch_shift(const float* x, int64_t B, int64_t L, int64_t stride, float* shift_dev, void* workspace,
+                    int64_t workspace_bytes, void* cuda_stream);
+/* aec_features with the two shifts read from DEVICE memory (NULL = 0) */
+int aec_features_dev(const float* mic, const float* ref, const float* erb, float* feat, int64_t B, int64_t L,
+                     int64_t in_stride, int32_t frame, int32_t bands, const float* shift_mic_dev,
+                     const float* shift_ref_dev, void* cuda_stream);
+
 /* Stage-2 residual-echo suppressor inference (the consumer of the stage-1 output), for the
  * reference's live model Little_net (Stage2_lhm/scripts/network/ERB.py:203-334, 32 ERB bands):
  *   feat = aec_features(stage1_error or mic, far, erb)                          ERB.py:254-290
@@ -200,6 +212,11 @@ int aec_stage2_mask(const float* feat, const aec_stage2_weights* w, float* est_e
 int aec_stage2_synth(const float* mic, const float* est_erb, const float* erb, float* out, int64_t B, int64_t L,
                      int64_t in_stride, int64_t out_stride, int32_t frame, int32_t bands, float shift_mic,
                      void* cuda_stream);
+
+/* aec_stage2_synth with the shift read from DEVICE memory (NULL = 0) */
+int aec_stage2_synth_dev(const float* mic, const float* est_erb, const float* erb, float* out, int64_t B, int64_t L,
+                         int64_t in_stride, int64_t out_stride, int32_t frame, int32_t bands, const float* shift_mic_dev,
+                         void* cuda_stream);
 
 /* Measurement helpers used by bench.py (not part of the reference-facing surface).
  * aec_bench_fp32_peak: dependent-free FFMA loop on every SM; returns achieved FP32 TFLOP/s. */

@@ -353,6 +353,21 @@ def test_full_batch_against_the_c_port_on_random_utterances():
         torch.cuda.empty_cache()
 
 
+def test_batch_shift_matches_torch_and_stays_on_the_device():
+    """ERB.py:254-256: mean / std (unbiased) over the whole batch tensor, reduced on the device (no host sync)"""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for shape, off in (((7, 4099), 0.01), ((64, 160000), -0.003), ((1, 513), 0.2)):
+        x = 0.1 * torch.randn(shape, device="cuda", generator=g) + off
+        s = A.batch_shift(x)
+        assert s.is_cuda and s.shape == (1,)
+        want = (x.double().mean() / x.double().std()).item()
+        assert abs(s.item() - want) <= 2e-6 * max(1.0, abs(want))
+        assert torch.equal(s, A.batch_shift(x))                       # fixed summation order: bitwise repeatable
+    xs = torch.empty(5, 5000, device="cuda")[:, :4097]                # strided rows, odd length -> scalar path
+    xs.copy_(0.05 * torch.randn(5, 4097, device="cuda", generator=g) + 0.02)
+    assert abs(A.batch_shift(xs).item() - (xs.double().mean() / xs.double().std()).item()) <= 1e-6
+
+
 def test_unsupported_combination_is_reported_not_emulated():
     d = synth.make_batch(0, 1, 4096)
     with pytest.raises(A.AecError) as ei:
