@@ -132,8 +132,9 @@ def main():
     warm = types.SimpleNamespace(train_path=os.path.join(work, f"warm{rank}"), h5_path=os.path.join(work, f"warm_h5_{rank}"),
                                  list_path=os.path.join(work, f"warm_l_{rank}"), sr=sr)
     os.makedirs(warm.list_path, exist_ok=True)
-    # (as many utterances as every rank's shard of them is one full batch: the page-locked buffers get their final size)
-    link_ids(pool_dir, warm.train_path, args.pool, 10 ** 9 + rank * 100000, args.batch * world)
+    # (every rank's shard of them is three full batches: all three decoder buffer sets and both output sets of the
+    #  runner get their final size -- page-locked allocations are slow and would otherwise land in the timed run)
+    link_ids(pool_dir, warm.train_path, args.pool, 10 ** 9 + rank * 100000, 3 * args.batch * world)
     wav2h5.create_h5_train(warm, runner=runner, batch=args.batch, h5=store, decode_threads=dthreads,
                            write_threads=wthreads, pinned=True)
     if world > 1:
