@@ -16,7 +16,9 @@
  * statement by statement.
  *
  * The reference computes each DFT as a dense [2K x N] convolution; this port uses an FFT
- * (same result to float32 rounding) so that the CPU baseline is not handicapped.
+ * (same result to float32 rounding) so that the CPU baseline is not handicapped.  Since round 2 the transforms run
+ * eight frames at a time in structure-of-arrays form and the recurrence is written as loops over the bins, so that the
+ * compiler vectorises both (AVX2 / AVX-512 via -march=native); OpenMP parallelises over utterances.
  */
 #include <math.h>
 #include <stdint.h>
@@ -87,168 +89,250 @@ static void plan_destroy(plan* p) {
     free(p->tw); free(p->tw_n); free(p->rev); free(p->win); free(p->norm); free(p);
 }
 
-/* in-place radix-2 DIT complex FFT of length m; sign = -1 forward, +1 inverse (unscaled) */
-static void fft_c(const plan* p, cpx* a, int sign) {
+/* ---- transforms, SIMD across VL frames at a time ------------------------------------------------------------
+ * In-place radix-2 DIT complex FFT of length m (sign = -1 forward, +1 inverse, unscaled) on the layout [point][VL]:
+ * every butterfly is applied to VL independent frames at once, so the compiler can use full-width vector instructions.
+ * A real frame of n samples is one complex FFT of n/2 points (even samples real lane, odd samples imaginary lane)
+ * plus the usual split into K = n/2+1 bins (rfft convention, attention_ccrn.py:15-18); the inverse packs the bins
+ * back (imaginary parts of DC / Nyquist ignored).  (Round-2 change, VERDICT r1 weak 7: no scalar FFT in the CPU arm.) */
+#define VL 8
+
+static void fft_c_v(const plan* p, float* restrict re, float* restrict im, int sign) {
     const int m = p->m;
     for (int i = 0; i < m; ++i) {
         const int r = p->rev[i];
-        if (r > i) { cpx t = a[i]; a[i] = a[r]; a[r] = t; }
+        if (r > i) {
+            for (int l = 0; l < VL; ++l) {
+                float t = re[i * VL + l]; re[i * VL + l] = re[r * VL + l]; re[r * VL + l] = t;
+                t = im[i * VL + l]; im[i * VL + l] = im[r * VL + l]; im[r * VL + l] = t;
+            }
+        }
     }
     for (int len = 2; len <= m; len <<= 1) {
         const int half = len >> 1, step = m / len;
         for (int s = 0; s < m; s += len) {
             for (int j = 0; j < half; ++j) {
                 const cpx w = p->tw[j * step];
-                const float wi = sign < 0 ? w.im : -w.im;
-                const cpx u = a[s + j], v = a[s + j + half];
-                const float tr = v.re * w.re - v.im * wi;
-                const float ti = v.re * wi + v.im * w.re;
-                a[s + j].re = u.re + tr; a[s + j].im = u.im + ti;
-                a[s + j + half].re = u.re - tr; a[s + j + half].im = u.im - ti;
+                const float wr = w.re, wi = sign < 0 ? w.im : -w.im;
+                float* restrict ur = re + (size_t)(s + j) * VL;
+                float* restrict ui = im + (size_t)(s + j) * VL;
+                float* restrict vr = re + (size_t)(s + j + half) * VL;
+                float* restrict vi = im + (size_t)(s + j + half) * VL;
+#pragma omp simd
+                for (int l = 0; l < VL; ++l) {
+                    const float tr = vr[l] * wr - vi[l] * wi;
+                    const float ti = vr[l] * wi + vi[l] * wr;
+                    const float a = ur[l], b = ui[l];
+                    ur[l] = a + tr; ui[l] = b + ti;
+                    vr[l] = a - tr; vi[l] = b - ti;
+                }
             }
         }
     }
-}
-
-/* windowed real frame (n samples) -> K = n/2+1 bins, rfft convention (attention_ccrn.py:15-18) */
-static void rfft_frame(const plan* p, const float* x, cpx* out, cpx* work) {
-    const int m = p->m;
-    for (int i = 0; i < m; ++i) { work[i].re = x[2 * i]; work[i].im = x[2 * i + 1]; }
-    fft_c(p, work, -1);
-    for (int k = 0; k <= m; ++k) {
-        const cpx a = work[k & (m - 1)], b = work[(m - k) & (m - 1)];
-        const float er = 0.5f * (a.re + b.re), ei = 0.5f * (a.im - b.im);   /* even part */
-        const float orr = 0.5f * (a.im + b.im), oi = 0.5f * (b.re - a.re);  /* odd part  */
-        const cpx w = p->tw_n[k];
-        out[k].re = er + (orr * w.re - oi * w.im);
-        out[k].im = ei + (orr * w.im + oi * w.re);
-    }
-    out[0].im = 0.f;
-    out[m].im = 0.f;
-}
-
-/* K bins -> n real samples (irfft; imaginary parts of DC / Nyquist ignored) */
-static void irfft_frame(const plan* p, const cpx* in, float* x, cpx* work) {
-    const int m = p->m;
-    for (int k = 0; k < m; ++k) {
-        cpx a = in[k], b = in[m - k];
-        if (k == 0) { a.im = 0.f; b.im = 0.f; }
-        const float er = a.re + b.re, ei = a.im - b.im;           /* E[k] + conj E[m-k] */
-        const float dr = a.re - b.re, di = a.im + b.im;           /* E[k] - conj E[m-k] */
-        const cpx w = p->tw_n[k];                                 /* multiply by conj(w) */
-        const float tr = dr * w.re + di * w.im, ti = di * w.re - dr * w.im;
-        work[k].re = er - ti;
-        work[k].im = ei + tr;
-    }
-    fft_c(p, work, +1);
-    const float s = 1.0f / (float)p->n;
-    for (int i = 0; i < m; ++i) { x[2 * i] = work[i].re * s; x[2 * i + 1] = work[i].im * s; }
 }
 
 /* one utterance */
 static void run_one(const plan* p, const aec_oracle_cfg* cfg, const float* far, const float* mic, int64_t n,
                     int64_t out_len_total, float* err, float* echo, float* erle_db) {
-    const int N = p->n, H = N / 2, K = H + 1, P = cfg->partitions;
+    const int N = p->n, H = N / 2, K = H + 1, P = cfg->partitions, m = H;
+    const int KP = (K + 15) & ~15;                   /* padded row length of the per-bin arrays */
     const int64_t T = n / H + 1;                     /* attention_ccrn.py:48-49 with N = 2H */
     const int64_t valid = (T - 1) * H;
-    cpx* W = (cpx*)calloc((size_t)P * K, sizeof(cpx));
-    cpx* hist = (cpx*)calloc((size_t)P * K, sizeof(cpx));   /* ring: slot (t - p) mod P */
-    float* C = (float*)malloc(sizeof(float) * (size_t)P * K);
-    float* psi = (float*)calloc((size_t)K, sizeof(float));
-    cpx* X = (cpx*)malloc(sizeof(cpx) * (size_t)K);
-    cpx* Y = (cpx*)malloc(sizeof(cpx) * (size_t)K);
-    cpx* E = (cpx*)malloc(sizeof(cpx) * (size_t)K);
-    cpx* Yh = (cpx*)malloc(sizeof(cpx) * (size_t)K);
-    cpx* work = (cpx*)malloc(sizeof(cpx) * (size_t)H);
+    /* per-bin state, structure of arrays: [tap][bin] */
+    float* Wr = (float*)calloc((size_t)P * KP, sizeof(float));
+    float* Wi = (float*)calloc((size_t)P * KP, sizeof(float));
+    float* Hr = (float*)calloc((size_t)P * KP, sizeof(float));   /* far-end history ring: slot (t - q) mod P */
+    float* Hi = (float*)calloc((size_t)P * KP, sizeof(float));
+    float* C = (float*)malloc(sizeof(float) * (size_t)P * KP);
+    float* cx2 = (float*)malloc(sizeof(float) * (size_t)P * KP);
+    float* psi = (float*)calloc((size_t)KP, sizeof(float));
+    /* spectra of the VL frames of a chunk: [frame][bin] */
+    float* Yr = (float*)malloc(sizeof(float) * (size_t)VL * KP);
+    float* Yi = (float*)malloc(sizeof(float) * (size_t)VL * KP);
+    float* Xr = (float*)malloc(sizeof(float) * (size_t)VL * KP);
+    float* Xi = (float*)malloc(sizeof(float) * (size_t)VL * KP);
+    float* Er = (float*)malloc(sizeof(float) * (size_t)VL * KP);
+    float* Ei = (float*)malloc(sizeof(float) * (size_t)VL * KP);
+    float* Yhr = (float*)malloc(sizeof(float) * (size_t)VL * KP);
+    float* Yhi = (float*)malloc(sizeof(float) * (size_t)VL * KP);
+    float* wre = (float*)malloc(sizeof(float) * (size_t)m * VL);  /* transform workspace [point][VL] */
+    float* wim = (float*)malloc(sizeof(float) * (size_t)m * VL);
     float* fr = (float*)malloc(sizeof(float) * (size_t)N);
     float* prev_e = (float*)calloc((size_t)H, sizeof(float));   /* windowed second half of frame t-1 */
     float* prev_y = (float*)calloc((size_t)H, sizeof(float));
-    float* cx2 = (float*)malloc(sizeof(float) * (size_t)P);
-    for (int i = 0; i < P * K; ++i) C[i] = cfg->kalman_c0;
+    float* yr = (float*)malloc(sizeof(float) * (size_t)KP);
+    float* yi = (float*)malloc(sizeof(float) * (size_t)KP);
+    float* pw = (float*)malloc(sizeof(float) * (size_t)KP);
+    for (int i = 0; i < P * KP; ++i) C[i] = cfg->kalman_c0;
     const float A = cfg->kalman_a, A2 = A * A, Q = (float)(1.0 - (double)A * (double)A);
     const float lam = cfg->kalman_lambda, oml = 1.0f - lam;
+    const float mu = cfg->mu, delta = cfg->delta, keps = cfg->kalman_eps;
     double pm = 0.0, pe = 0.0;
 
-    for (int64_t t = 0; t < T; ++t) {
-        /* ---- analysis (zero padded by H on the left, zeros beyond n on the right) ---- */
+    for (int64_t t0 = 0; t0 < T; t0 += VL) {
+        const int nf = (int)((T - t0) < VL ? (T - t0) : VL);
+        /* ---- analysis of the chunk's frames (zero padded by H on the left, zeros beyond n on the right) ---- */
         for (int s = 0; s < 2; ++s) {
             const float* src = s == 0 ? far : mic;
-            for (int i = 0; i < N; ++i) {
-                const int64_t idx = (t - 1) * H + i;
-                fr[i] = (idx >= 0 && idx < n) ? src[idx] * p->win[i] : 0.f;
-            }
-            rfft_frame(p, fr, s == 0 ? X : Y, work);
-        }
-        cpx* slot = hist + (size_t)(t % P) * K;
-        memcpy(slot, X, sizeof(cpx) * (size_t)K);
-        /* ---- recurrence, per bin ---- */
-        for (int k = 0; k < K; ++k) {
-            float yr = 0.f, yi = 0.f;
-            for (int q = 0; q < P; ++q) {
-                const cpx x = hist[(size_t)((t - q + 4 * (int64_t)P) % P) * K + k];   /* X[t-q], zero before start */
-                const cpx w = W[(size_t)q * K + k];
-                yr += w.re * x.re - w.im * x.im;
-                yi += w.re * x.im + w.im * x.re;
-            }
-            const float er = Y[k].re - yr, ei = Y[k].im - yi;
-            if (cfg->algo == 0) {
-                float pw = 0.f;
-                for (int q = 0; q < P; ++q) {
-                    const cpx x = hist[(size_t)((t - q + 4 * (int64_t)P) % P) * K + k];
-                    pw += x.re * x.re + x.im * x.im;
+            float* outr = s == 0 ? Xr : Yr;
+            float* outi = s == 0 ? Xi : Yi;
+            for (int f = 0; f < VL; ++f) {
+                const int64_t t = t0 + f;
+                for (int i = 0; i < m; ++i) {
+                    const int64_t i0 = (t - 1) * H + 2 * i, i1 = i0 + 1;
+                    wre[i * VL + f] = (f < nf && i0 >= 0 && i0 < n) ? src[i0] * p->win[2 * i] : 0.f;
+                    wim[i * VL + f] = (f < nf && i1 >= 0 && i1 < n) ? src[i1] * p->win[2 * i + 1] : 0.f;
                 }
-                const float g = cfg->mu / (pw + cfg->delta);
-                const float gr = g * er, gi = g * ei;
+            }
+            fft_c_v(p, wre, wim, -1);
+            for (int k = 0; k <= m; ++k) {                        /* rfft_frame's split, VL frames at once */
+                const int ka = k & (m - 1), kb = (m - k) & (m - 1);
+                const cpx w = p->tw_n[k];
+                for (int f = 0; f < VL; ++f) {
+                    const float ar = wre[ka * VL + f], ai = wim[ka * VL + f];
+                    const float br = wre[kb * VL + f], bi = wim[kb * VL + f];
+                    const float er = 0.5f * (ar + br), ei = 0.5f * (ai - bi);
+                    const float orr = 0.5f * (ai + bi), oi = 0.5f * (br - ar);
+                    outr[f * KP + k] = er + (orr * w.re - oi * w.im);
+                    outi[f * KP + k] = (k == 0 || k == m) ? 0.f : ei + (orr * w.im + oi * w.re);
+                }
+            }
+        }
+        /* ---- recurrence: frames in order, every statement a loop over the bins ---- */
+        for (int f = 0; f < nf; ++f) {
+            const int64_t t = t0 + f;
+            const float* restrict xr = Xr + (size_t)f * KP;
+            const float* restrict xi = Xi + (size_t)f * KP;
+            const float* restrict yyr = Yr + (size_t)f * KP;
+            const float* restrict yyi = Yi + (size_t)f * KP;
+            float* restrict er = Er + (size_t)f * KP;
+            float* restrict ei = Ei + (size_t)f * KP;
+            float* restrict hr0 = Hr + (size_t)(t % P) * KP;
+            float* restrict hi0 = Hi + (size_t)(t % P) * KP;
+            memcpy(hr0, xr, sizeof(float) * (size_t)K);
+            memcpy(hi0, xi, sizeof(float) * (size_t)K);
+#pragma omp simd
+            for (int k = 0; k < K; ++k) { yr[k] = 0.f; yi[k] = 0.f; }
+            for (int q = 0; q < P; ++q) {
+                const float* restrict hr = Hr + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;   /* X[t-q], zero before start */
+                const float* restrict hi = Hi + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;
+                const float* restrict wr = Wr + (size_t)q * KP;
+                const float* restrict wi = Wi + (size_t)q * KP;
+#pragma omp simd
+                for (int k = 0; k < K; ++k) {
+                    yr[k] += wr[k] * hr[k] - wi[k] * hi[k];
+                    yi[k] += wr[k] * hi[k] + wi[k] * hr[k];
+                }
+            }
+#pragma omp simd
+            for (int k = 0; k < K; ++k) { er[k] = yyr[k] - yr[k]; ei[k] = yyi[k] - yi[k]; }
+            if (cfg->algo == 0) {
+#pragma omp simd
+                for (int k = 0; k < K; ++k) pw[k] = 0.f;
                 for (int q = 0; q < P; ++q) {
-                    const cpx x = hist[(size_t)((t - q + 4 * (int64_t)P) % P) * K + k];
-                    cpx* w = &W[(size_t)q * K + k];
-                    w->re += x.re * gr + x.im * gi;      /* conj(x) * g e */
-                    w->im += x.re * gi - x.im * gr;
+                    const float* restrict hr = Hr + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;
+                    const float* restrict hi = Hi + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;
+#pragma omp simd
+                    for (int k = 0; k < K; ++k) pw[k] += hr[k] * hr[k] + hi[k] * hi[k];
+                }
+#pragma omp simd
+                for (int k = 0; k < K; ++k) pw[k] = mu / (pw[k] + delta);           /* g */
+                for (int q = 0; q < P; ++q) {
+                    const float* restrict hr = Hr + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;
+                    const float* restrict hi = Hi + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;
+                    float* restrict wr = Wr + (size_t)q * KP;
+                    float* restrict wi = Wi + (size_t)q * KP;
+#pragma omp simd
+                    for (int k = 0; k < K; ++k) {
+                        const float gr = pw[k] * er[k], gi = pw[k] * ei[k];
+                        wr[k] += hr[k] * gr + hi[k] * gi;      /* conj(x) * g e */
+                        wi[k] += hr[k] * gi - hi[k] * gr;
+                    }
                 }
             } else {
-                const float e2 = er * er + ei * ei;
-                psi[k] = lam * psi[k] + oml * e2;
-                float d = 0.f;
-                for (int q = 0; q < P; ++q) {
-                    const cpx x = hist[(size_t)((t - q + 4 * (int64_t)P) % P) * K + k];
-                    cx2[q] = C[(size_t)q * K + k] * (x.re * x.re + x.im * x.im);
-                    d += cx2[q];
+#pragma omp simd
+                for (int k = 0; k < K; ++k) {
+                    const float e2 = er[k] * er[k] + ei[k] * ei[k];
+                    psi[k] = lam * psi[k] + oml * e2;
+                    pw[k] = 0.f;                                                     /* d */
                 }
-                d = d + psi[k] + cfg->kalman_eps;
-                const float rd = 1.0f / d;
                 for (int q = 0; q < P; ++q) {
-                    const cpx x = hist[(size_t)((t - q + 4 * (int64_t)P) % P) * K + k];
-                    float* c = &C[(size_t)q * K + k];
-                    cpx* w = &W[(size_t)q * K + k];
-                    const float gs = *c * rd;
-                    const float gr = gs * x.re, gi = -gs * x.im;
-                    const float wr = A * (w->re + gr * er - gi * ei);
-                    const float wi = A * (w->im + gr * ei + gi * er);
-                    w->re = wr; w->im = wi;
-                    *c = A2 * (1.0f - cx2[q] * rd) * *c + Q * (wr * wr + wi * wi);
+                    const float* restrict hr = Hr + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;
+                    const float* restrict hi = Hi + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;
+                    const float* restrict c = C + (size_t)q * KP;
+                    float* restrict cx = cx2 + (size_t)q * KP;
+#pragma omp simd
+                    for (int k = 0; k < K; ++k) {
+                        cx[k] = c[k] * (hr[k] * hr[k] + hi[k] * hi[k]);
+                        pw[k] += cx[k];
+                    }
                 }
-            }
-            E[k].re = er; E[k].im = ei;
-            Yh[k].re = yr; Yh[k].im = yi;
-        }
-        /* ---- synthesis + overlap-add: output hop t-1 = second half of frame t-1 + first half of t ---- */
-        for (int s = 0; s < (echo ? 2 : 1); ++s) {
-            float* prev = s == 0 ? prev_e : prev_y;
-            float* dst = s == 0 ? err : echo;
-            irfft_frame(p, s == 0 ? E : Yh, fr, work);
-            for (int i = 0; i < N; ++i) fr[i] *= p->win[i];
-            if (t >= 1) {
-                for (int j = 0; j < H; ++j) {
-                    const float o = (prev[j] + fr[j]) * p->norm[j];
-                    dst[(t - 1) * H + j] = o;
-                    if (s == 0 && t - 1 >= cfg->erle_skip_hops) {
-                        const float mv = mic[(t - 1) * H + j];
-                        pe += (double)o * o;
-                        pm += (double)mv * mv;
+#pragma omp simd
+                for (int k = 0; k < K; ++k) pw[k] = 1.0f / (pw[k] + psi[k] + keps);   /* rd */
+                for (int q = 0; q < P; ++q) {
+                    const float* restrict hr = Hr + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;
+                    const float* restrict hi = Hi + (size_t)((t - q + 4 * (int64_t)P) % P) * KP;
+                    float* restrict c = C + (size_t)q * KP;
+                    const float* restrict cx = cx2 + (size_t)q * KP;
+                    float* restrict wr = Wr + (size_t)q * KP;
+                    float* restrict wi = Wi + (size_t)q * KP;
+#pragma omp simd
+                    for (int k = 0; k < K; ++k) {
+                        const float gs = c[k] * pw[k];
+                        const float gr = gs * hr[k], gi = -gs * hi[k];
+                        const float nr = A * (wr[k] + gr * er[k] - gi * ei[k]);
+                        const float ni = A * (wi[k] + gr * ei[k] + gi * er[k]);
+                        wr[k] = nr; wi[k] = ni;
+                        c[k] = A2 * (1.0f - cx[k] * pw[k]) * c[k] + Q * (nr * nr + ni * ni);
                     }
                 }
             }
-            memcpy(prev, fr + H, sizeof(float) * (size_t)H);
+            memcpy(Yhr + (size_t)f * KP, yr, sizeof(float) * (size_t)K);
+            memcpy(Yhi + (size_t)f * KP, yi, sizeof(float) * (size_t)K);
+        }
+        /* ---- synthesis of the chunk + overlap-add: output hop t-1 = second half of frame t-1 + first half of t ---- */
+        for (int s = 0; s < (echo ? 2 : 1); ++s) {
+            const float* inr = s == 0 ? Er : Yhr;
+            const float* ini = s == 0 ? Ei : Yhi;
+            float* prev = s == 0 ? prev_e : prev_y;
+            float* dst = s == 0 ? err : echo;
+            for (int k = 0; k < m; ++k) {                         /* irfft_frame's packing, VL frames at once */
+                const cpx w = p->tw_n[k];
+                for (int f = 0; f < VL; ++f) {
+                    float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+                    if (f < nf) {
+                        ar = inr[f * KP + k]; ai = ini[f * KP + k];
+                        br = inr[f * KP + m - k]; bi = ini[f * KP + m - k];
+                        if (k == 0) { ai = 0.f; bi = 0.f; }
+                    }
+                    const float e_r = ar + br, e_i = ai - bi;
+                    const float dr = ar - br, di = ai + bi;
+                    const float tr = dr * w.re + di * w.im, ti = di * w.re - dr * w.im;
+                    wre[k * VL + f] = e_r - ti;
+                    wim[k * VL + f] = e_i + tr;
+                }
+            }
+            fft_c_v(p, wre, wim, +1);
+            const float sc = 1.0f / (float)p->n;
+            for (int f = 0; f < nf; ++f) {
+                const int64_t t = t0 + f;
+                for (int i = 0; i < m; ++i) {
+                    fr[2 * i] = wre[i * VL + f] * sc * p->win[2 * i];
+                    fr[2 * i + 1] = wim[i * VL + f] * sc * p->win[2 * i + 1];
+                }
+                if (t >= 1) {
+                    for (int j = 0; j < H; ++j) {
+                        const float o = (prev[j] + fr[j]) * p->norm[j];
+                        dst[(t - 1) * H + j] = o;
+                        if (s == 0 && t - 1 >= cfg->erle_skip_hops) {
+                            const float mv = mic[(t - 1) * H + j];
+                            pe += (double)o * o;
+                            pm += (double)mv * mv;
+                        }
+                    }
+                }
+                memcpy(prev, fr + H, sizeof(float) * (size_t)H);
+            }
         }
     }
     for (int64_t i = valid; i < out_len_total; ++i) {
@@ -260,8 +344,9 @@ static void run_one(const plan* p, const aec_oracle_cfg* cfg, const float* far, 
         if (pe < 1e-20) pe = 1e-20;
         *erle_db = (float)(10.0 * log10(pm / pe));
     }
-    free(W); free(hist); free(C); free(psi); free(X); free(Y); free(E); free(Yh); free(work); free(fr);
-    free(prev_e); free(prev_y); free(cx2);
+    free(Wr); free(Wi); free(Hr); free(Hi); free(C); free(cx2); free(psi); free(Yr); free(Yi); free(Xr); free(Xi);
+    free(Er); free(Ei); free(Yhr); free(Yhi); free(wre); free(wim); free(fr); free(prev_e); free(prev_y);
+    free(yr); free(yi); free(pw);
 }
 
 /* Batch entry.  Buffers are host float32; n_samples nullable.  n_threads <= 0 -> all cores.
