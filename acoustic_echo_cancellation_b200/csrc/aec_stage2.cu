@@ -21,31 +21,34 @@ constexpr int kIn = 64;         // 2 * bands
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
-// One warp per utterance, lane j = hidden unit / band j.  Weights are staged transposed in shared
-// memory (groups of four inputs per unit, 16-byte loads); the frame's feature
-// vector and the hidden state are broadcast through a per-warp scratch.
+// One warp per utterance, lane j = hidden unit / band j, CH = 8 frames per chunk (round 2: only what depends on h stays
+// on the frame-to-frame chain):
+//   phase 1  W_ih x_t + b for the chunk's 8 frames at once -- no dependence on h, 24 independent accumulators per lane,
+//            every weight load (float4 groups of four inputs per unit, staged transposed in shared memory) used 8 times;
+//   phase 2  the recurrence proper: W_hh h_{t-1} with lane j's three rows of W_hh held in REGISTERS (96 floats), the hidden
+//            state broadcast through 32 floats of shared memory (8 x LDS.128), gates, h_t -> per-chunk buffer;
+//   phase 3  Linear(64->32)+ReLU on cat[h_t, mic_erb_t] and Linear(32->32)+sigmoid for the 8 frames at once, mask * mic_erb.
+// Before, every step ran all 18.4 k multiply-adds of the three layers (and ~400 shared-memory wavefronts of weights) as one
+// dependent chain on a single warp: ~3 400 cycles per frame; the chain is now ~1/6 of that.
+constexpr int kCh = 8;
+constexpr int kScratch = kCh * kIn + 2 * kCh * kH + kH;   // floats per warp: xs[8][64] + hb[8][32] + os[8][32] + hs[32]
+
 template <int kMaskWarps>
 __global__ void __launch_bounds__(kMaskWarps * 32) stage2_mask_kernel(const float* __restrict__ feat,
                                                                       aec_stage2_weights w, float* __restrict__ est,
                                                                       long long B, long long T) {
     extern __shared__ __align__(16) float sm[];
-    float* wih = sm;                       // [64][96]
-    float* whh = wih + kIn * 96;           // [32][96]
-    float* w1 = whh + kH * 96;             // [64][32]
-    float* w2 = w1 + kIn * kH;             // [32][32]
+    float* wih = sm;                       // [3][16][32][4]
+    float* w1 = wih + kIn * 96;            // [16][32][4]
+    float* w2 = w1 + kIn * kH;             // [8][32][4]
     float* bias = w2 + kH * kH;            // b_ih[96] b_hh[96] b1[32] b2[32]
-    float* scratch = bias + 256;           // per warp: x[64] h[32] o2[32]
+    float* scratch = bias + 256;           // per warp: kScratch floats
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // weights as float4 groups of four consecutive inputs per (gate, unit): one 16-byte load feeds four FFMAs
-    //   wih : [gate 3][input/4 16][unit 32][4]     whh : [gate 3][input/4 8][unit 32][4]
-    //   w1  : [input/4 16][unit 32][4]             w2  : [input/4 8][unit 32][4]
+    //   wih : [gate 3][input/4 16][unit 32][4]     w1 : [input/4 16][unit 32][4]     w2 : [input/4 8][unit 32][4]
     for (int i = tid; i < 96 * kIn; i += blockDim.x) {
         const int row = i / kIn, col = i % kIn, g = row >> 5, j = row & 31;
         wih[(((g * (kIn / 4) + (col >> 2)) * 32 + j) << 2) + (col & 3)] = __ldg(w.gru_w_ih + i);
-    }
-    for (int i = tid; i < 96 * kH; i += blockDim.x) {
-        const int row = i / kH, col = i % kH, g = row >> 5, j = row & 31;
-        whh[(((g * (kH / 4) + (col >> 2)) * 32 + j) << 2) + (col & 3)] = __ldg(w.gru_w_hh + i);
     }
     for (int i = tid; i < kH * kIn; i += blockDim.x) {
         const int j = i / kIn, col = i % kIn;
@@ -66,76 +69,119 @@ __global__ void __launch_bounds__(kMaskWarps * 32) stage2_mask_kernel(const floa
     __syncthreads();
     const long long b = (long long)blockIdx.x * kMaskWarps + warp;
     if (b >= B) return;
-    float* xs = scratch + warp * 128;
-    float* hs = xs + 64;
-    float* os = xs + 96;
+    float* xs = scratch + warp * kScratch;          // [kCh][64] the chunk's feature vectors
+    float* hb = xs + kCh * kIn;                      // [kCh][32] h_t of the chunk
+    float* os = hb + kCh * kH;                       // [kCh][32] linear1 outputs
+    float* hs = os + kCh * kH;                       // [32]      h_{t-1}, broadcast buffer of the recurrence
     const float* fb = feat + b * T * kIn;
     float* eb = est + b * T * kH;
     const float b_r = bias[lane] + bias[96 + lane], b_z = bias[32 + lane] + bias[128 + lane];
     const float b_in = bias[64 + lane], b_hn = bias[160 + lane];
     const float b_1 = bias[192 + lane], b_2 = bias[224 + lane];
+    // lane j's rows of W_hh (gate order r, z, n), resident in registers for the whole utterance
+    float whr[kH], whz[kH], whn[kH];
+#pragma unroll
+    for (int i = 0; i < kH; ++i) {
+        whr[i] = __ldg(w.gru_w_hh + (0 * kH + lane) * kH + i);
+        whz[i] = __ldg(w.gru_w_hh + (1 * kH + lane) * kH + i);
+        whn[i] = __ldg(w.gru_w_hh + (2 * kH + lane) * kH + i);
+    }
+    const float4* wih4 = reinterpret_cast<const float4*>(wih) + lane;
+    const float4* w14 = reinterpret_cast<const float4*>(w1) + lane;
+    const float4* w24 = reinterpret_cast<const float4*>(w2) + lane;
+    const float4* hs4 = reinterpret_cast<const float4*>(hs);
     float h = 0.f;
-    hs[lane] = 0.f;
-    float x0 = T > 0 ? __ldg(fb + lane) : 0.f, x1 = T > 0 ? __ldg(fb + 32 + lane) : 0.f;
-    for (long long t = 0; t < T; ++t) {
+    for (long long t0 = 0; t0 < T; t0 += kCh) {
+        const int nf = (int)((T - t0) < kCh ? (T - t0) : kCh);
         __syncwarp();
-        xs[lane] = x0;
-        xs[32 + lane] = x1;
-        const float merb = x0;                       // lane j: mic_erb[j] (first half of the feature vector)
-        __syncwarp();
-        if (t + 1 < T) {                             // prefetch the next frame's features
-            x0 = __ldg(fb + (t + 1) * kIn + lane);
-            x1 = __ldg(fb + (t + 1) * kIn + 32 + lane);
+        // ---- stage the chunk's feature vectors (coalesced; frames past the end read as zero) ----
+#pragma unroll
+        for (int r = 0; r < 2 * kCh; ++r) {
+            const int f = r >> 1, col = lane + 32 * (r & 1);
+            xs[f * kIn + col] = (f < nf) ? __ldg(fb + (t0 + f) * kIn + col) : 0.f;
         }
-        // four partial sums per gate (one per position inside a group of four inputs): the recurrence is latency-bound
-        // on one warp, and a single accumulator per gate made every step a chain of 96 dependent FFMAs
-        float ar[4] = {b_r, 0.f, 0.f, 0.f}, az[4] = {b_z, 0.f, 0.f, 0.f}, ain[4] = {b_in, 0.f, 0.f, 0.f},
-              ahn[4] = {b_hn, 0.f, 0.f, 0.f};
-        const float4* wih4 = reinterpret_cast<const float4*>(wih) + lane;
-        const float4* whh4 = reinterpret_cast<const float4*>(whh) + lane;
-#pragma unroll 4
+        __syncwarp();
+        // ---- phase 1: input projections of the chunk ----
+        float gr[kCh], gz[kCh], gn[kCh];
+#pragma unroll
+        for (int f = 0; f < kCh; ++f) {
+            gr[f] = b_r;
+            gz[f] = b_z;
+            gn[f] = b_in;
+        }
+#pragma unroll 2
         for (int i4 = 0; i4 < kIn / 4; ++i4) {
-            const float4 xv = *reinterpret_cast<const float4*>(xs + 4 * i4);
             const float4 wr = wih4[(0 * (kIn / 4) + i4) * 32], wz = wih4[(1 * (kIn / 4) + i4) * 32], wn = wih4[(2 * (kIn / 4) + i4) * 32];
-            ar[0] = fmaf(wr.x, xv.x, ar[0]); ar[1] = fmaf(wr.y, xv.y, ar[1]); ar[2] = fmaf(wr.z, xv.z, ar[2]); ar[3] = fmaf(wr.w, xv.w, ar[3]);
-            az[0] = fmaf(wz.x, xv.x, az[0]); az[1] = fmaf(wz.y, xv.y, az[1]); az[2] = fmaf(wz.z, xv.z, az[2]); az[3] = fmaf(wz.w, xv.w, az[3]);
-            ain[0] = fmaf(wn.x, xv.x, ain[0]); ain[1] = fmaf(wn.y, xv.y, ain[1]); ain[2] = fmaf(wn.z, xv.z, ain[2]); ain[3] = fmaf(wn.w, xv.w, ain[3]);
+#pragma unroll
+            for (int f = 0; f < kCh; ++f) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + f * kIn + 4 * i4);
+                gr[f] = fmaf(wr.w, xv.w, fmaf(wr.z, xv.z, fmaf(wr.y, xv.y, fmaf(wr.x, xv.x, gr[f]))));
+                gz[f] = fmaf(wz.w, xv.w, fmaf(wz.z, xv.z, fmaf(wz.y, xv.y, fmaf(wz.x, xv.x, gz[f]))));
+                gn[f] = fmaf(wn.w, xv.w, fmaf(wn.z, xv.z, fmaf(wn.y, xv.y, fmaf(wn.x, xv.x, gn[f]))));
+            }
         }
-#pragma unroll 4
-        for (int i4 = 0; i4 < kH / 4; ++i4) {
-            const float4 hv = *reinterpret_cast<const float4*>(hs + 4 * i4);
-            const float4 wr = whh4[(0 * (kH / 4) + i4) * 32], wz = whh4[(1 * (kH / 4) + i4) * 32], wn = whh4[(2 * (kH / 4) + i4) * 32];
-            ar[0] = fmaf(wr.x, hv.x, ar[0]); ar[1] = fmaf(wr.y, hv.y, ar[1]); ar[2] = fmaf(wr.z, hv.z, ar[2]); ar[3] = fmaf(wr.w, hv.w, ar[3]);
-            az[0] = fmaf(wz.x, hv.x, az[0]); az[1] = fmaf(wz.y, hv.y, az[1]); az[2] = fmaf(wz.z, hv.z, az[2]); az[3] = fmaf(wz.w, hv.w, az[3]);
-            ahn[0] = fmaf(wn.x, hv.x, ahn[0]); ahn[1] = fmaf(wn.y, hv.y, ahn[1]); ahn[2] = fmaf(wn.z, hv.z, ahn[2]); ahn[3] = fmaf(wn.w, hv.w, ahn[3]);
+        // ---- phase 2: the recurrence (the only serial part) ----
+#pragma unroll
+        for (int f = 0; f < kCh; ++f) {
+            if (f < nf) {
+                hs[lane] = h;
+                __syncwarp();
+                // four partial sums per gate: twelve independent chains of eight FFMAs
+                float ar[4] = {0.f, 0.f, 0.f, 0.f}, az[4] = {0.f, 0.f, 0.f, 0.f}, an[4] = {b_hn, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i4 = 0; i4 < kH / 4; ++i4) {
+                    const float4 hv = hs4[i4];
+                    ar[0] = fmaf(whr[4 * i4 + 0], hv.x, ar[0]); ar[1] = fmaf(whr[4 * i4 + 1], hv.y, ar[1]);
+                    ar[2] = fmaf(whr[4 * i4 + 2], hv.z, ar[2]); ar[3] = fmaf(whr[4 * i4 + 3], hv.w, ar[3]);
+                    az[0] = fmaf(whz[4 * i4 + 0], hv.x, az[0]); az[1] = fmaf(whz[4 * i4 + 1], hv.y, az[1]);
+                    az[2] = fmaf(whz[4 * i4 + 2], hv.z, az[2]); az[3] = fmaf(whz[4 * i4 + 3], hv.w, az[3]);
+                    an[0] = fmaf(whn[4 * i4 + 0], hv.x, an[0]); an[1] = fmaf(whn[4 * i4 + 1], hv.y, an[1]);
+                    an[2] = fmaf(whn[4 * i4 + 2], hv.z, an[2]); an[3] = fmaf(whn[4 * i4 + 3], hv.w, an[3]);
+                }
+                const float r = sigmoidf_(gr[f] + ((ar[0] + ar[1]) + (ar[2] + ar[3])));
+                const float z = sigmoidf_(gz[f] + ((az[0] + az[1]) + (az[2] + az[3])));
+                const float n = tanhf(fmaf(r, (an[0] + an[1]) + (an[2] + an[3]), gn[f]));
+                h = fmaf(z, h - n, n);                   // (1 - z) n + z h
+                hb[f * kH + lane] = h;
+                __syncwarp();                            // every lane has read hs before the next step overwrites it
+            } else {
+                hb[f * kH + lane] = 0.f;
+            }
         }
-        const float r = sigmoidf_((ar[0] + ar[1]) + (ar[2] + ar[3])), z = sigmoidf_((az[0] + az[1]) + (az[2] + az[3]));
-        const float n = tanhf(fmaf(r, (ahn[0] + ahn[1]) + (ahn[2] + ahn[3]), (ain[0] + ain[1]) + (ain[2] + ain[3])));
-        h = fmaf(z, h - n, n);                       // (1 - z) n + z h
         __syncwarp();
-        hs[lane] = h;
-        __syncwarp();
-        float a1[4] = {b_1, 0.f, 0.f, 0.f}, a1x[4] = {0.f, 0.f, 0.f, 0.f};   // linear1 on cat[h, mic_erb]  (ERB.py:295-298)
-        const float4* w14 = reinterpret_cast<const float4*>(w1) + lane;
-#pragma unroll 4
+        // ---- phase 3: linear1 on cat[h, mic_erb] + ReLU, linear2 + sigmoid, mask * mic_erb (ERB.py:295-304) ----
+        float a1[kCh];
+#pragma unroll
+        for (int f = 0; f < kCh; ++f) a1[f] = b_1;
+#pragma unroll 2
         for (int i4 = 0; i4 < kH / 4; ++i4) {
-            const float4 hv = *reinterpret_cast<const float4*>(hs + 4 * i4);
-            const float4 xv = *reinterpret_cast<const float4*>(xs + 4 * i4);
             const float4 wa = w14[i4 * 32], wb = w14[(kH / 4 + i4) * 32];      // inputs 0..31 = h, 32..63 = mic_erb
-            a1[0] = fmaf(wa.x, hv.x, a1[0]); a1[1] = fmaf(wa.y, hv.y, a1[1]); a1[2] = fmaf(wa.z, hv.z, a1[2]); a1[3] = fmaf(wa.w, hv.w, a1[3]);
-            a1x[0] = fmaf(wb.x, xv.x, a1x[0]); a1x[1] = fmaf(wb.y, xv.y, a1x[1]); a1x[2] = fmaf(wb.z, xv.z, a1x[2]); a1x[3] = fmaf(wb.w, xv.w, a1x[3]);
+#pragma unroll
+            for (int f = 0; f < kCh; ++f) {
+                const float4 hv = *reinterpret_cast<const float4*>(hb + f * kH + 4 * i4);
+                const float4 xv = *reinterpret_cast<const float4*>(xs + f * kIn + 4 * i4);
+                a1[f] = fmaf(wa.w, hv.w, fmaf(wa.z, hv.z, fmaf(wa.y, hv.y, fmaf(wa.x, hv.x, a1[f]))));
+                a1[f] = fmaf(wb.w, xv.w, fmaf(wb.z, xv.z, fmaf(wb.y, xv.y, fmaf(wb.x, xv.x, a1[f]))));
+            }
         }
-        os[lane] = fmaxf(((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1x[0] + a1x[1]) + (a1x[2] + a1x[3])), 0.f);
+#pragma unroll
+        for (int f = 0; f < kCh; ++f) os[f * kH + lane] = fmaxf(a1[f], 0.f);
         __syncwarp();
-        float a2[4] = {b_2, 0.f, 0.f, 0.f};          // linear2 + sigmoid  (ERB.py:301)
-        const float4* w24 = reinterpret_cast<const float4*>(w2) + lane;
-#pragma unroll 4
+        float a2[kCh];
+#pragma unroll
+        for (int f = 0; f < kCh; ++f) a2[f] = b_2;
+#pragma unroll 2
         for (int i4 = 0; i4 < kH / 4; ++i4) {
-            const float4 ov = *reinterpret_cast<const float4*>(os + 4 * i4);
             const float4 wv = w24[i4 * 32];
-            a2[0] = fmaf(wv.x, ov.x, a2[0]); a2[1] = fmaf(wv.y, ov.y, a2[1]); a2[2] = fmaf(wv.z, ov.z, a2[2]); a2[3] = fmaf(wv.w, ov.w, a2[3]);
+#pragma unroll
+            for (int f = 0; f < kCh; ++f) {
+                const float4 ov = *reinterpret_cast<const float4*>(os + f * kH + 4 * i4);
+                a2[f] = fmaf(wv.w, ov.w, fmaf(wv.z, ov.z, fmaf(wv.y, ov.y, fmaf(wv.x, ov.x, a2[f]))));
+            }
         }
-        eb[t * kH + lane] = sigmoidf_((a2[0] + a2[1]) + (a2[2] + a2[3])) * merb;    // est_erb = mask * mic_erb  (ERB.py:304)
+#pragma unroll
+        for (int f = 0; f < kCh; ++f)
+            if (f < nf) eb[(t0 + f) * kH + lane] = sigmoidf_(a2[f]) * xs[f * kIn + lane];   // est_erb = mask * mic_erb
     }
 }
 
@@ -290,7 +336,7 @@ extern "C" int aec_stage2_mask(const float* feat, const aec_stage2_weights* w, f
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     auto launch = [&](auto warps_tag) -> int {
         constexpr int kW = decltype(warps_tag)::value;
-        const size_t smem = (size_t)(kIn * 96 + kH * 96 + kIn * kH + kH * kH + 256 + kW * 128) * sizeof(float);
+        const size_t smem = (size_t)(kIn * 96 + kIn * kH + kH * kH + 256 + kW * kScratch) * sizeof(float);
         AEC_CUDA_CHECK(cudaFuncSetAttribute(stage2_mask_kernel<kW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)((B + kW - 1) / kW);
         stage2_mask_kernel<kW><<<grid, kW * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(feat, *w, est_erb, B, T);

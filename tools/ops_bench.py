@@ -95,6 +95,24 @@ def main():
 
     o_ours, o_ref = net(x, y), ref_stage2(x, y)
     res["stage2_inference_ms"] = {"ours": timeit(lambda: net(x, y), 5), "torch_cudnn_restatement": timeit(lambda: ref_stage2(x, y), 5)}
+    # the three launches of the inference separately (same buffers, in_norm shifts precomputed)
+    import ctypes as C
+
+    from acoustic_echo_cancellation_b200 import _lib
+    lib = _lib.load()
+    T = A.num_frames(L)
+    sm_, sr_ = A.batch_shift(x), A.batch_shift(y)
+    feat = A.stage2_features(x, y, erb, shifts=(sm_, sr_))
+    est = torch.empty((B, T, 32), device="cuda")
+    outb = torch.empty((B, A.out_samples(L)), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    res["stage2_parts_ms"] = {
+        "batch_shift_x2": timeit(lambda: (A.batch_shift(x), A.batch_shift(y))),
+        "features": timeit(lambda: A.stage2_features(x, y, erb, shifts=(sm_, sr_))),
+        "mask_gru_linears": timeit(lambda: lib.aec_stage2_mask(feat.data_ptr(), C.byref(net._cw), est.data_ptr(), B, T, 32, st)),
+        "synth": timeit(lambda: lib.aec_stage2_synth_dev(x.data_ptr(), est.data_ptr(), net.erb.data_ptr(), outb.data_ptr(), B, L, L,
+                                                         outb.shape[1], 512, 32, sm_.data_ptr(), st)),
+    }
     n_cmp = min(o_ours.shape[1], o_ref.shape[1])
     res["max_abs_diff"]["stage2"] = float((o_ours[:, :n_cmp] - o_ref[:, :n_cmp]).abs().max())
     res["stage2_out_scale"] = float(o_ref.abs().max())
