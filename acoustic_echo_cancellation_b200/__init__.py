@@ -8,13 +8,14 @@ CPU fallback.  See DESIGN.md / INTEGRATION.md.
 """
 from ._lib import ALGO_KALMAN, ALGO_NLMS, AecError, LIB_PATH  # noqa: F401
 from .stage1 import (HOST_PORTABLE, HOST_WRITE_COMBINED, HostPipeline, Stage1Config, fp32_peak_tflops,  # noqa: F401
-                     is_pinned, launch_count, num_frames, out_samples, pinned_empty, stage1_aec)
+                     is_pinned, launch_count, num_frames, out_samples, pinned_empty, stage1_aec,
+                     stage1_aec_features)
 from .spectral import ConvSTFT, ConviSTFT, batch_shift, erb_filterbank, stage2_features  # noqa: F401
 from .stage2 import LittleNetInference  # noqa: F401
 
 __all__ = [
     "ALGO_KALMAN", "ALGO_NLMS", "AecError", "LIB_PATH", "HostPipeline", "Stage1Config", "fp32_peak_tflops",
     "launch_count", "num_frames", "out_samples", "pinned_empty", "is_pinned", "HOST_WRITE_COMBINED",
-    "HOST_PORTABLE", "stage1_aec", "ConvSTFT", "ConviSTFT",
+    "HOST_PORTABLE", "stage1_aec", "stage1_aec_features", "ConvSTFT", "ConviSTFT",
     "erb_filterbank", "stage2_features", "batch_shift", "LittleNetInference",
 ]

@@ -286,14 +286,18 @@ static long long* g_phase_buffer = nullptr;
 extern "C" void aec_debug_set_phase_buffer(void* p) { g_phase_buffer = static_cast<long long*>(p); }
 #endif
 
-extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, float* echo_est, float* erle_db,
-                              const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride, int64_t out_stride,
-                              const aec_cfg* cfg, void* cuda_stream) {
+static int stage1_run_impl(const float* far, const float* mic, float* err, float* echo_est, float* erle_db,
+                           const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride, int64_t out_stride,
+                           const aec_cfg* cfg, void* cuda_stream, float* feat, const float* erb) {
     int rc = validate_cfg(cfg);
     if (rc != AEC_OK) return rc;
     if (B < 0 || L < 0 || in_stride < L || out_stride < L) return AEC_EINVAL;
     if (B == 0) return AEC_OK;
     if (!far || !mic || !err) return AEC_EINVAL;
+    if (feat) {
+        if (!erb || echo_est) return AEC_EINVAL;
+        if (cfg->frame != 512) return AEC_EUNSUPPORTED;      // the reference's ERB configuration is 257 bins
+    }
     if (B > 0x7fffffffLL || L > 0x3fffffffLL) return AEC_EINVAL;
     Tables tab;
     rc = get_tables(&tab);
@@ -321,6 +325,9 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
     p.kc0 = cfg->kalman_c0;
     p.keps = cfg->kalman_eps;
     p.erle_skip_hops = cfg->erle_skip_hops;
+    p.feat = feat;
+    p.erb = erb;
+    p.feat_frames = aec_num_frames(L, cfg->frame);
 #ifdef AEC_PHASE_TIMING
     p.dbg = g_phase_buffer;
 #endif
@@ -357,7 +364,9 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
         //  128 registers for the two-warp kernels so that 7 utterances stay resident per SM)
     }
     cudaError_t e;
-    if (wide) {
+    if (feat) {
+        e = launch_stage1_feat(P, cfg->algo, p, s);
+    } else if (wide) {
         e = launch_stage1_1024(P, cfg->algo, echo, minb, p, s);
     } else
     switch (nw) {
@@ -374,6 +383,21 @@ extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, fl
     }
     count_launch();
     return AEC_OK;
+}
+
+extern "C" int aec_stage1_run(const float* far, const float* mic, float* err, float* echo_est, float* erle_db,
+                              const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride, int64_t out_stride,
+                              const aec_cfg* cfg, void* cuda_stream) {
+    return stage1_run_impl(far, mic, err, echo_est, erle_db, n_samples, B, L, in_stride, out_stride, cfg, cuda_stream,
+                           nullptr, nullptr);
+}
+
+extern "C" int aec_stage1_run_features(const float* far, const float* mic, float* err, float* erle_db, float* feat,
+                                       const float* erb, const int64_t* n_samples, int64_t B, int64_t L,
+                                       int64_t in_stride, int64_t out_stride, const aec_cfg* cfg, void* cuda_stream) {
+    if (!feat || !erb) return AEC_EINVAL;
+    return stage1_run_impl(far, mic, err, nullptr, erle_db, n_samples, B, L, in_stride, out_stride, cfg, cuda_stream, feat,
+                           erb);
 }
 
 // ------------------------------------------------------------------------------------------

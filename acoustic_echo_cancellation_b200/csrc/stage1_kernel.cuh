@@ -59,6 +59,10 @@ struct Stage1Params {
     const float2* tw512;   // [129]     exp(-2 pi i k / 512)
     const float2* win_a;   // [256]     0.5 * hann[2m], 0.5 * hann[2m+1]
     const float2* win_s;   // [256]     hann[n] / (512 * (coff[n] + 1e-8)), n = 2m, 2m+1
+    // fused Stage-2 feature epilogue (FEAT instantiations only; Stage2_lhm/scripts/network/ERB.py:262-290, in_norm off)
+    float* feat;           // [B][feat_frames][64]  cat[err_erb, |err_erb - far_erb|]
+    const float* erb;      // [257][32] dense cosine bank (ERB.py:10-71), device memory
+    long long feat_frames; // rows per utterance (frames of an L-sample signal)
 #ifdef AEC_PHASE_TIMING
     long long* dbg;        // developer build only: [B][NW][12] cycles per phase (tools/phase_timing.py)
 #endif
@@ -286,11 +290,16 @@ struct Stage1Smem {
     __host__ __device__ static constexpr size_t total(bool echo) {
         return zbuf_bytes + stage_bytes + win_bytes + tails_bytes(echo) + mid_bytes + ring_bytes + 16;
     }
+    // fused feature epilogue: error-signal blocks [F+1][256], magnitudes of E' and X [2][F][kMagPitch], far-end band
+    // energies [8][32], band-major non-zero bank coefficients [512], per-band sum / first bin / length / offset [4][32]
+    static constexpr int kMagPitch = 260;
+    static constexpr size_t feat_bytes = (size_t(F + 1) * 256 + size_t(2) * F * kMagPitch + 8 * 32 + 512 + 4 * 32) * sizeof(float);
+    __host__ __device__ static constexpr size_t total_feat(bool echo) { return total(echo) + feat_bytes; }
 };
 
 // REGS caps the registers per thread (occupancy knob: resident utterances per SM =
 // 65536 / (32 * NW * REGS), also bounded by shared memory).
-template <int NW, int P, int ALGO, bool ECHO, int REGS>
+template <int NW, int P, int ALGO, bool ECHO, int REGS, bool FEAT = false>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(const Stage1Params prm) {
     using SM = Stage1Smem<NW, P>;
     constexpr bool kRing = SM::kRing;
@@ -302,6 +311,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     constexpr int PPT = kSingleBin ? 1 : 128 / (kSingleBin ? 128 : NT);   // mirrored pairs per thread
     constexpr int NBIN = kSingleBin ? 1 : 2 * PPT;                        // bins per thread
     static_assert(NW == 1 || NW == 2 || NW == 4 || NW == 8, "1, 2, 4 or 8 warps per utterance");
+    static_assert(!FEAT || (NW == 2 && !kRing), "the fused feature epilogue is built on the two-warp kernel");
     constexpr int NSIG = ECHO ? 2 : 1;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -315,6 +325,18 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                                               SM::tails_bytes(ECHO) + SM::mid_bytes);        // [P][kRingPitch]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::zbuf_bytes + SM::stage_bytes + SM::win_bytes +
                                                  SM::tails_bytes(ECHO) + SM::mid_bytes + SM::ring_bytes);
+
+    // fused Stage-2 feature epilogue (FEAT): see feat_epilogue below
+    constexpr int kMagPitch = SM::kMagPitch;
+    float* f_ring = reinterpret_cast<float*>(smem_raw + SM::total(ECHO));   // [F+1][256]  error-signal blocks, slot = block % (F+1)
+    float* f_magE = f_ring + (F + 1) * 256;                                 // [F][kMagPitch]  |STFT(err)| of frames t0-1 .. t0+F-2
+    float* f_magX = f_magE + F * kMagPitch;                                 // [F][kMagPitch]  |X| of the chunk's frames
+    float* f_xerb = f_magX + F * kMagPitch;                                 // [8][32]   far-end band energies, slot = frame & 7
+    float* f_cb = f_xerb + 8 * 32;                                          // [512]     non-zero bank coefficients, band-major
+    float* f_csum = f_cb + 512;                                             // [32]      band energy of a silent frame
+    int* f_lo = reinterpret_cast<int*>(f_csum + 32);                        // [32]      first bin of the band
+    int* f_len = f_lo + 32;                                                 // [32]      bins in the band
+    int* f_off = f_len + 32;                                                // [32]      offset into f_cb
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, h = lane & 15;
@@ -432,6 +454,38 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     }
     for (int i = tid; i < 128; i += NT) win_a[i] = __ldg(&prm.win_a[i]);
     for (int i = tid; i < 256; i += NT) win_s[i] = __ldg(&prm.win_s[i]);
+    if constexpr (FEAT) {
+        // the cosine bank is ~2 non-zeros per bin (483 of 257 x 32 for the reference's bank): keep each band's non-zero
+        // range contiguously, so that a projection is a short loop over [lo, lo + len) instead of a dense product
+        if (tid < 32) {
+            int lo = 257, hi = 0;
+            for (int k = 0; k < 257; ++k)
+                if (__ldg(prm.erb + k * 32 + tid) != 0.f) {
+                    lo = lo < k ? lo : k;
+                    hi = k + 1;
+                }
+            const int len = hi > lo ? hi - lo : 0;
+            int off = len;                               // inclusive prefix sum over the bands
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, off, o);
+                if (lane >= o) off += v;
+            }
+            off -= len;
+            const int keep = off + len <= 512 ? len : (off < 512 ? 512 - off : 0);   // (host side rejects larger banks)
+            float cs = 0.f;
+            const float silent = sqrtf(1e-9f);           // magnitude of an all-zero frame (ERB.py:277-278)
+            for (int i = 0; i < keep; ++i) {
+                const float c = __ldg(prm.erb + (lo + i) * 32 + tid);
+                f_cb[off + i] = c;
+                cs = fmaf(silent, c, cs);
+            }
+            f_lo[tid] = len ? lo : 0;
+            f_len[tid] = keep;
+            f_off[tid] = off < 512 ? off : 0;
+            f_csum[tid] = cs;
+        }
+    }
     TwiddleRegs twr;
     twr.w1 = __ldg(&prm.tw256[1 * 16 + h]);
     twr.w2 = __ldg(&prm.tw256[2 * 16 + h]);
@@ -646,6 +700,96 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         if (warp >= F / 2) mid_ahead(0, 0u);
     }
 
+    // ---- fused Stage-2 feature epilogue, parity-preserving form -----------------------------
+    // The reference front end takes STFTs of TIME-DOMAIN signals (ERB.py:262-264).  The error spectrum E the filter holds
+    // is not the STFT of the error signal it synthesises (overlap-add + re-analysis projects it; measured 48 % median
+    // difference of the band energies), so the epilogue re-analyses the synthesised error hops --
+    // which are on chip in phase C -- one frame behind the synthesis: frame tau of STFT(err) needs output blocks tau and
+    // tau + 1.  The far-end band energies come from |X| of the analysis the filter already did.  Per chunk:
+    //   phase D   4 half-warps = 4 frames tau = t0-1 .. t0+2: window the error blocks, FFT-256, unpack, magnitudes
+    //   project   lane pair (2j, 2j+1) owns band j: two frames each of |X| (this chunk) and |STFT(err)| (one behind),
+    //             a loop over the band's non-zero bins; feat[tau] = cat[err_erb, |err_erb - far_erb|]
+    // `in_norm` (the batch-global mean / std shift of ERB.py:254-256) is off in this path: the shift of the error signal
+    // is not known before the whole batch has been processed (aec_features[_dev] on the stored error signal covers it).
+    auto feat_epilogue = [&](int t0) {
+      if constexpr (FEAT) {
+        {
+            const int hw = 2 * warp + half;
+            const int tau = t0 - 1 + hw;
+            const bool live = tau >= 0 && tau <= T - 1;
+            float2 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int beta = tau + (j >> 3);                       // block beta = output hop beta - 1; 0 and T are zero pads
+                const bool ok = live && beta >= 1 && beta <= T - 1;
+                float2 x = make_float2(0.f, 0.f);
+                if (ok) x = *reinterpret_cast<const float2*>(f_ring + (beta % (F + 1)) * 256 + 2 * h + 32 * (j & 7));
+                float2 w = win_a[h + 16 * (j & 7)];
+                if (j >= 8) w = make_float2(0.5f - w.x, 0.5f - w.y);
+                v[j] = make_float2(x.x * w.x, x.y * w.y);
+            }
+            float2* tile = zbuf + (hw * 2 + 1) * kTilePitch;           // (every spectrum tile is dead by now)
+            fft256_halfwarp_regs<false>(v, tile, twr, h);
+#pragma unroll
+            for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
+            __syncwarp();
+            if (live) {
+                float* me = f_magE + hw * kMagPitch;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = h + 16 * q;
+                    float2 xk, xm;
+                    unpack_pair(tile[k], tile[(256 - k) & 255], __ldg(&prm.tw512[k]), xk, xm);
+                    if (k == 0) {
+                        xk.y = 0.f;
+                        xm.y = 0.f;
+                    }
+                    me[k] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));        // ERB.py:277-278
+                    me[256 - k] = sqrtf(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
+                }
+                if (h == 0) {
+                    float2 xk, xm;
+                    unpack_pair(tile[128], tile[128], make_float2(0.f, -1.f), xk, xm);
+                    me[128] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const int j = tid >> 1, fp = tid & 1;
+            const int lo = f_lo[j], len = f_len[j];
+            const float* c = f_cb + f_off[j];
+            const float* mx0 = f_magX + (2 * fp) * kMagPitch + lo;
+            const float* mx1 = mx0 + kMagPitch;
+            const float* me0 = f_magE + (2 * fp) * kMagPitch + lo;
+            const float* me1 = me0 + kMagPitch;
+            float ax0 = 0.f, ax1 = 0.f, ae0 = 0.f, ae1 = 0.f;
+            for (int i = 0; i < len; ++i) {                            // ERB.py:282-283, ascending bins
+                const float cc = c[i];
+                ax0 = fmaf(mx0[i], cc, ax0);
+                ax1 = fmaf(mx1[i], cc, ax1);
+                ae0 = fmaf(me0[i], cc, ae0);
+                ae1 = fmaf(me1[i], cc, ae1);
+            }
+            const int tx = t0 + 2 * fp;                                // far-end frames of this chunk
+            if (tx < T) f_xerb[(tx & 7) * 32 + j] = ax0;
+            if (tx + 1 < T) f_xerb[((tx + 1) & 7) * 32 + j] = ax1;
+            __syncwarp();                                              // the pair partner's far-end energies
+            float* fb = prm.feat + (static_cast<long long>(blockIdx.x) * prm.feat_frames) * 64;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int tau = t0 - 1 + 2 * fp + r;
+                if (tau >= 0 && tau <= T - 1 && tau < prm.feat_frames) {
+                    const float e = r ? ae1 : ae0;
+                    const float xe = f_xerb[(tau & 7) * 32 + j];
+                    fb[static_cast<long long>(tau) * 64 + j] = e;
+                    fb[static_cast<long long>(tau) * 64 + 32 + j] = fabsf(e - xe);   // ERB.py:287-290
+                }
+            }
+        }
+      }
+    };
+
     float acc_e = 0.f;     // ERLE energies in ONE register: lanes 16-31 accumulate the microphone, lanes 0-15 the error
 
     // (chunk count not kept in a register: every use is a comparison of the frame index with T)
@@ -747,6 +891,11 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     float2 xk, xm, yk, ym, ek, em, hk, hm, gk, gm;
                     unpack_pair(zf[k], zf[km], wk[i], xk, xm);
                     unpack_pair(zm[k], zm[km], wk[i], yk, ym);
+                    if constexpr (FEAT) {                 // |X| for the far-end band energies (bins k and 256 - k)
+                        float* mx = f_magX + tl * kMagPitch;
+                        mx[k] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
+                        mx[256 - k] = sqrtf(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
+                    }
                     bin_step<P, ALGO>(st[2 * i], xk, yk, prm, ek, hk);
                     bin_step<P, ALGO>(st[2 * i + 1], xm, ym, prm, em, hm);
                     // (k == 0 is the DC / Nyquist pair: X, Y are exactly real there, so W, E and Yhat stay
@@ -768,6 +917,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                         const float2 fa = zf[128], ma = zm[128];
                         unpack_pair(fa, fa, w_mid, xk, xm);
                         unpack_pair(ma, ma, w_mid, yk, ym);
+                        if constexpr (FEAT) f_magX[tl * kMagPitch + 128] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
                         BinState<P, ALGO> st_mid;
                         st_mid.load(mid_state);
                         bin_step<P, ALGO>(st_mid, xk, yk, prm, ek, hk);
@@ -895,6 +1045,10 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                 if (st_ok && vec) st_stream_f2(dst + 32 * r, o);
                 if (st_ok && !vec) { st_stream_f1(dst + 32 * r, o.x); st_stream_f1(dst + 32 * r + 1, o.y); }
                 en = fmaf(o.x, o.x, fmaf(o.y, o.y, en));
+                if constexpr (FEAT) {                  // output block t + 1 of the error signal stays on chip for the re-analysis
+                    if (lower && sgn == 0)
+                        *reinterpret_cast<float2*>(f_ring + ((t + 1) % (F + 1)) * 256 + 2 * h + 32 * r) = o;
+                }
                 if (!lower) tail_dst[h + 16 * r] = u[8 + r];
                 // unconditional: a predicated assignment would make the old value loop-carried
                 // (16 registers live across the whole chunk loop -> spills)
@@ -925,6 +1079,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     if (vec) st_stream_f2(dst + 32 * r, o);
                     else { st_stream_f1(dst + 32 * r, o.x); st_stream_f1(dst + 32 * r + 1, o.y); }
                     en = fmaf(o.x, o.x, fmaf(o.y, o.y, en));
+                    if constexpr (FEAT) {              // output block t
+                        if (sgn == 0) *reinterpret_cast<float2*>(f_ring + (t % (F + 1)) * 256 + 2 * h + 32 * r) = o;
+                    }
                 }
                 if (sgn == 0 && t - 1 >= prm.erle_skip_hops) acc_e += en;
             }
@@ -940,6 +1097,20 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                 for (int i = 0; i < 4; ++i) carry[sgn * 128 + lane + 32 * i] = src[lane + 32 * i];
             }
         }
+        if constexpr (FEAT) {
+            __syncthreads();                 // the chunk's error blocks are complete, every spectrum tile is dead
+            feat_epilogue(t0);
+        }
+    }
+    if constexpr (FEAT) {
+        // frames the one-frame lag left behind (at most F of them: the last chunk emitted up to its third frame) ...
+        const int t_last = ((T - 1) / F) * F;
+        __syncthreads();
+        feat_epilogue(t_last + F);
+        // ... and rows beyond this utterance's frames: what the front end gives for silence (ragged batches)
+        float* fb = prm.feat + (static_cast<long long>(blockIdx.x) * prm.feat_frames) * 64;
+        for (long long i = static_cast<long long>(T) * 64 + tid; i < prm.feat_frames * 64; i += NT)
+            fb[i] = (i & 32) ? 0.f : f_csum[i & 31];
     }
 
 #ifdef AEC_PHASE_TIMING

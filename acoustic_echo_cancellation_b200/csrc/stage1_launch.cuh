@@ -17,10 +17,13 @@ cudaError_t launch_stage1_nw2(int P, int algo, bool echo, int regs, const Stage1
 cudaError_t launch_stage1_nw4(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
 cudaError_t launch_stage1_nw8(int P, int algo, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
 
-template <int NW, int P_, int ALGO, bool ECHO, int REGS>
+// stage 1 with the fused Stage-2 feature epilogue (stage1_inst_feat.cu)
+cudaError_t launch_stage1_feat(int P, int algo, const Stage1Params& prm, cudaStream_t s);
+
+template <int NW, int P_, int ALGO, bool ECHO, int REGS, bool FEAT = false>
 inline cudaError_t launch_stage1_instance(const Stage1Params& prm, cudaStream_t s) {
-    auto kern = stage1_n512_kernel<NW, P_, ALGO, ECHO, REGS>;
-    const size_t smem = Stage1Smem<NW, P_>::total(ECHO);
+    auto kern = stage1_n512_kernel<NW, P_, ALGO, ECHO, REGS, FEAT>;
+    const size_t smem = FEAT ? Stage1Smem<NW, P_>::total_feat(ECHO) : Stage1Smem<NW, P_>::total(ECHO);
     static thread_local int configured_dev = -1;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);

@@ -129,6 +129,64 @@ def stage1_aec(far: torch.Tensor, mic: torch.Tensor, cfg: Optional[Stage1Config]
     return res[0] if len(res) == 1 else tuple(res)
 
 
+def stage1_aec_features(far: torch.Tensor, mic: torch.Tensor, erb: torch.Tensor, cfg: Optional[Stage1Config] = None,
+                        n_samples: Optional[torch.Tensor] = None, return_erle: bool = False,
+                        out: Optional[torch.Tensor] = None):
+    """Stage 1 with the Stage-2 feature front end fused into the kernel (``aec_stage1_run_features``).
+
+    Returns ``(err [B, L], feat [B, T, 64])`` (+ ``erle_db [B]``): ``feat`` is what
+    ``stage2_features(err, far, erb, in_norm=False)`` gives -- ``cat[err_erb, |err_erb - far_erb|]`` of
+    Little_net.forward (Stage2_lhm/scripts/network/ERB.py:262-290) with the stage-1 error in the microphone's place --
+    without re-reading ``err`` and ``far`` from HBM and without a second far-end STFT.  ``erb``: [257, 32] float32 CUDA."""
+    cfg = cfg or Stage1Config()
+    _require_cuda_f32("far", far)
+    _require_cuda_f32("mic", mic)
+    _require_cuda_f32("erb", erb)
+    if far.dim() == 1:
+        far, mic = far[None], mic[None]
+    if far.shape != mic.shape or far.dim() != 2 or far.device != mic.device:
+        raise ValueError("far and mic must be [B, L] tensors of equal shape on one device")
+    if tuple(erb.shape) != (257, 32):
+        raise ValueError("erb must be [257, 32]")
+    key = (erb.data_ptr(), erb._version)
+    if key not in _checked_banks:
+        nz = erb != 0
+        idx = torch.arange(257, device=erb.device)[:, None].expand(257, 32)
+        span = torch.where(nz, idx, torch.full_like(idx, -1)).amax(0) - torch.where(nz, idx, torch.full_like(idx, 10 ** 6)).amin(0) + 1
+        if int(span.clamp(min=0).sum()) > 512:
+            raise ValueError("the ERB bank has more than 512 coefficients inside its bands' non-zero ranges")
+        _checked_banks.add(key)
+    if far.stride(1) != 1 or mic.stride(1) != 1 or far.stride(0) != mic.stride(0):
+        far, mic = far.contiguous(), mic.contiguous()
+    erb = erb.contiguous()
+    B, L = far.shape
+    in_stride = far.stride(0) if B > 1 else max(far.stride(0), L)
+    lib = _lib.load()
+    with torch.cuda.device(far.device):
+        if out is None:
+            out = torch.empty((B, L), dtype=torch.float32, device=far.device)
+        elif out.shape != (B, L) or not out.is_cuda or out.dtype != torch.float32 or out.stride(1) != 1:
+            raise ValueError("out must be a [B, L] float32 CUDA tensor with unit inner stride")
+        feat = torch.empty((B, num_frames(L, cfg.frame), 64), dtype=torch.float32, device=far.device)
+        erle = torch.empty((B,), dtype=torch.float32, device=far.device) if return_erle else None
+        ns_ptr = None
+        if n_samples is not None:
+            n_samples = n_samples.to(device=far.device, dtype=torch.int64).contiguous()
+            if n_samples.numel() != B:
+                raise ValueError("n_samples must have B entries")
+            ns_ptr = n_samples.data_ptr()
+        out_stride = out.stride(0) if B > 1 else max(out.stride(0), L)
+        c = cfg.to_c()
+        rc = lib.aec_stage1_run_features(far.data_ptr(), mic.data_ptr(), out.data_ptr(),
+                                         erle.data_ptr() if erle is not None else None, feat.data_ptr(), erb.data_ptr(),
+                                         ns_ptr, B, L, in_stride, out_stride, C.byref(c), _stream_ptr(far))
+        _lib.check(rc, "aec_stage1_run_features")
+    return (out, feat, erle) if return_erle else (out, feat)
+
+
+_checked_banks = set()
+
+
 class HostPipeline:
     """Host-buffer entry (``aec_stage1_run_host``; ``aec_stage1_run_host_pcm16`` for int16 PCM inputs,
     scaled by 1/32768 on the GPU): numpy arrays in, numpy arrays out, copies pipelined against the kernel

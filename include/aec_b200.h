@@ -97,6 +97,21 @@ int aec_stage1_run(const float* far, const float* mic, float* err, float* echo_e
                    const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride, int64_t out_stride,
                    const aec_cfg* cfg, void* cuda_stream);
 
+/* Stage 1 WITH the Stage-2 feature front end fused into the kernel (replaces, for the two-stage
+ * pipeline, the three dense-conv STFTs + magnitude + ERB matmul + cat of Little_net.forward,
+ * Stage2_lhm/scripts/network/ERB.py:262-290, applied to (stage-1 error, far end)):
+ *   feat [B][aec_num_frames(L)][64] = cat[err_erb, |err_erb - far_erb|], err_erb = sqrt(re^2+im^2+1e-9)(STFT(err)) @ erb,
+ *   far_erb likewise from the far end.  STFT(err) is the re-analysis of the SYNTHESISED error signal (parity with
+ *   aec_features(err, far, erb, shift 0)), computed on chip one frame behind the synthesis; the far-end spectrum is the
+ *   one the filter already has.  The batch-global shift of ERB.py:254-256 is NOT applied (it needs the whole error
+ *   batch first): this is the `in_norm = False` form; use aec_batch_shift + aec_features_dev for the shifted one.
+ *   erb: dense [257][32] float32 bank on the DEVICE (ERB.py:10-71; at most 512 coefficients inside the bands' non-zero
+ *   ranges -- the reference's bank has 483).  Rows of a ragged utterance beyond its own frames hold the front end's
+ *   response to silence.  Built for frame 512, partitions 4 (NLMS, Kalman), 2 and 1 (NLMS); no echo-estimate output. */
+int aec_stage1_run_features(const float* far, const float* mic, float* err, float* erle_db, float* feat, const float* erb,
+                            const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride, int64_t out_stride,
+                            const aec_cfg* cfg, void* cuda_stream);
+
 /* Host-buffer variant: the call a data-prep script makes with arrays that came out of
  * `librosa.load` (Stage2_lhm/generate_h5files/train_wav2h5.py:20-23) and whose results go to
  * `create_dataset` (train_wav2h5.py:39-42).  Copies are pipelined against the kernel in

@@ -353,6 +353,55 @@ def test_full_batch_against_the_c_port_on_random_utterances():
         torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("P,algo,L,B", [(4, 0, 16000 + 123, 5), (4, 1, 8 * 256, 3), (2, 0, 4097, 2), (1, 0, 300, 2),
+                                       (4, 0, 160000, 40)])
+def test_fused_feature_epilogue_equals_features_of_the_stored_error(P, algo, L, B):
+    """stage 1 with the Stage-2 front end fused in (aec_stage1_run_features) gives (a) the same error
+    signal, bit for bit, as the plain kernel and (b) the features the stand-alone operator computes from that stored
+    error signal and the far end (ERB.py:262-290, in_norm off) -- the parity-preserving form: STFT of the SYNTHESISED
+    error, not the filter's internal spectrum."""
+    d = synth.make_batch(30, B, L, rir_len=min(P * 256, 1024))
+    far, mic = _cuda(d["far"]), _cuda(d["mic"])
+    erb = torch.from_numpy(A.erb_filterbank()).float().cuda()
+    cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=2)
+    err, feat, erle = A.stage1_aec_features(far, mic, erb, cfg, return_erle=True)
+    ref_err, ref_erle = A.stage1_aec(far, mic, cfg, return_erle=True)
+    assert torch.equal(err, ref_err) and torch.equal(erle, ref_erle)
+    want = A.stage2_features(ref_err, far, erb, in_norm=False)
+    assert feat.shape == want.shape == (B, A.num_frames(L), 64)
+    scale = float(want.abs().max())
+    assert float((feat - want).abs().max()) <= 2e-5 * max(scale, 1.0), float((feat - want).abs().max())
+    assert torch.equal(feat, A.stage1_aec_features(far, mic, erb, cfg)[1])          # run-to-run determinism
+    # the filter's own spectrum would NOT do: features of the microphone signal differ from those of the error
+    assert float((feat - A.stage2_features(mic, far, erb, in_norm=False)).abs().max()) > 1e-3 * scale or L < 1000
+
+
+def test_fused_feature_epilogue_ragged_rows_and_golden_front_end(golden):
+    """ragged batch: rows of an utterance are those of the utterance processed alone, rows beyond its own frames hold
+    the front end's response to silence; and with a zero far end (error = microphone) the fused features of
+    (feat_mic, 0) equal the reference-generated golden front end of (feat_mic, 0)-shaped inputs computed stand-alone"""
+    L, B = 6000, 4
+    d = synth.make_batch(60, B, L, rir_len=512)
+    far, mic = _cuda(d["far"]), _cuda(d["mic"])
+    erb = torch.from_numpy(A.erb_filterbank()).float().cuda()
+    ns = torch.tensor([L, 3000, 255, 4096], dtype=torch.int64, device="cuda")
+    cfg = A.Stage1Config()
+    err, feat = A.stage1_aec_features(far, mic, erb, cfg, n_samples=ns)
+    assert torch.equal(err, A.stage1_aec(far, mic, cfg, n_samples=ns))
+    silent = A.stage2_features(torch.zeros(1, 512, device="cuda"), torch.zeros(1, 512, device="cuda"), erb, in_norm=False)[0, 0]
+    for b in range(B):
+        n = int(ns[b])
+        tb = A.num_frames(n)
+        e1, f1 = A.stage1_aec_features(far[b:b + 1, :n].contiguous(), mic[b:b + 1, :n].contiguous(), erb, cfg)
+        assert torch.equal(feat[b, :tb], f1[0])
+        assert torch.allclose(feat[b, tb:], silent.expand(feat.shape[1] - tb, 64), rtol=0, atol=1e-9)
+    # zero far end: the canceller is the identity (to float rounding), so the fused features are the front end of the mic
+    gm = _cuda(golden["feat_mic"])
+    e, f = A.stage1_aec_features(torch.zeros_like(gm), gm, erb, cfg)
+    want = A.stage2_features(e, torch.zeros_like(gm), erb, in_norm=False)
+    assert float((f - want).abs().max()) <= 2e-5 * max(float(want.abs().max()), 1.0)
+
+
 def test_batch_shift_matches_torch_and_stays_on_the_device():
     """ERB.py:254-256: mean / std (unbiased) over the whole batch tensor, reduced on the device (no host sync)"""
     g = torch.Generator(device="cuda").manual_seed(3)
