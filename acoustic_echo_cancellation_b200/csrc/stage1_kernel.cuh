@@ -290,10 +290,13 @@ struct Stage1Smem {
     __host__ __device__ static constexpr size_t total(bool echo) {
         return zbuf_bytes + stage_bytes + win_bytes + tails_bytes(echo) + mid_bytes + ring_bytes + 16;
     }
-    // fused feature epilogue: error-signal blocks [F+1][256], magnitudes of E' and X [2][F][kMagPitch], far-end band
-    // energies [8][32], band-major non-zero bank coefficients [512], per-band sum / first bin / length / offset [4][32]
+    // fused feature epilogue: error-signal blocks [F+1][256], |X| of the chunk's frames [F][kMagPitch] (|STFT(err)| goes
+    // into dead spectrum tiles), far-end band energies [F+1][32], band-major non-zero bank coefficients [512], per-band
+    // silent-frame energy / first task / task count [3][32], projection tasks [64] x (first bin, bins, coefficient offset)
+    // (the tasks' partial sums go into a dead tile too): 43.9 KB per utterance with the rest -> 5 utterances per SM
     static constexpr int kMagPitch = 260;
-    static constexpr size_t feat_bytes = (size_t(F + 1) * 256 + size_t(2) * F * kMagPitch + 8 * 32 + 512 + 4 * 32) * sizeof(float);
+    static constexpr size_t feat_bytes =
+        (size_t(F + 1) * 256 + size_t(F) * kMagPitch + (F + 1) * 32 + 512 + 3 * 32 + 3 * 64) * sizeof(float);
     __host__ __device__ static constexpr size_t total_feat(bool echo) { return total(echo) + feat_bytes; }
 };
 
@@ -329,14 +332,20 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     // fused Stage-2 feature epilogue (FEAT): see feat_epilogue below
     constexpr int kMagPitch = SM::kMagPitch;
     float* f_ring = reinterpret_cast<float*>(smem_raw + SM::total(ECHO));   // [F+1][256]  error-signal blocks, slot = block % (F+1)
-    float* f_magE = f_ring + (F + 1) * 256;                                 // [F][kMagPitch]  |STFT(err)| of frames t0-1 .. t0+F-2
-    float* f_magX = f_magE + F * kMagPitch;                                 // [F][kMagPitch]  |X| of the chunk's frames
-    float* f_xerb = f_magX + F * kMagPitch;                                 // [8][32]   far-end band energies, slot = frame & 7
-    float* f_cb = f_xerb + 8 * 32;                                          // [512]     non-zero bank coefficients, band-major
+    float* f_magX = f_ring + (F + 1) * 256;                                 // [F][kMagPitch]  |X| of the chunk's frames
+    float* f_xerb = f_magX + F * kMagPitch;                                 // [F+1][32] far-end band energies, slot = frame % (F+1)
+    float* f_cb = f_xerb + (F + 1) * 32;                                    // [512]     non-zero bank coefficients, band-major
     float* f_csum = f_cb + 512;                                             // [32]      band energy of a silent frame
-    int* f_lo = reinterpret_cast<int*>(f_csum + 32);                        // [32]      first bin of the band
-    int* f_len = f_lo + 32;                                                 // [32]      bins in the band
-    int* f_off = f_len + 32;                                                // [32]      offset into f_cb
+    int* f_tb0 = reinterpret_cast<int*>(f_csum + 32);                       // [32]      first projection task of the band
+    int* f_tbn = f_tb0 + 32;                                                // [32]      tasks of the band
+    int* f_tk = f_tbn + 32;                                                 // [64]      task: first bin
+    int* f_tn = f_tk + 64;                                                  // [64]      task: bins (0 = idle lane)
+    int* f_tc = f_tn + 64;                                                  // [64]      task: offset into f_cb
+    float* f_part = reinterpret_cast<float*>(zbuf + 1 * kTilePitch);         // [64][8]   partial band energies of the tasks: in the
+                                                                             //           first microphone tile, free after phase D
+    // |STFT(err)| of frame t0 - 1 + hw lives in the (dead) far-end tile of half-warp hw during the epilogue
+    auto mag_e = [&](int hw) { return reinterpret_cast<float*>(zbuf + (hw * 2 + 0) * kTilePitch); };
+    static_assert(!FEAT || kMagPitch * sizeof(float) <= kTilePitch * sizeof(float2), "magnitude row must fit a tile");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, h = lane & 15;
@@ -455,8 +464,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
     for (int i = tid; i < 128; i += NT) win_a[i] = __ldg(&prm.win_a[i]);
     for (int i = tid; i < 256; i += NT) win_s[i] = __ldg(&prm.win_s[i]);
     if constexpr (FEAT) {
-        // the cosine bank is ~2 non-zeros per bin (483 of 257 x 32 for the reference's bank): keep each band's non-zero
-        // range contiguously, so that a projection is a short loop over [lo, lo + len) instead of a dense product
+        // The cosine bank is ~2 non-zeros per bin (483 of 257 x 32 for the reference's bank).  Each band's non-zero range is
+        // staged contiguously, and the projection work is cut into at most 64 TASKS of equal length (a band and a run of
+        // its bins), one per thread: band-parallel, the 51-bin band would set the length of the loop for everybody.
         if (tid < 32) {
             int lo = 257, hi = 0;
             for (int k = 0; k < 257; ++k)
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     lo = lo < k ? lo : k;
                     hi = k + 1;
                 }
-            const int len = hi > lo ? hi - lo : 0;
+            int len = hi > lo ? hi - lo : 0;
             int off = len;                               // inclusive prefix sum over the bands
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -472,18 +482,42 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                 if (lane >= o) off += v;
             }
             off -= len;
-            const int keep = off + len <= 512 ? len : (off < 512 ? 512 - off : 0);   // (host side rejects larger banks)
+            len = off + len <= 512 ? len : (off < 512 ? 512 - off : 0);   // (the host side rejects larger banks)
+            off = off < 512 ? off : 0;
             float cs = 0.f;
             const float silent = sqrtf(1e-9f);           // magnitude of an all-zero frame (ERB.py:277-278)
-            for (int i = 0; i < keep; ++i) {
+            for (int i = 0; i < len; ++i) {
                 const float c = __ldg(prm.erb + (lo + i) * 32 + tid);
                 f_cb[off + i] = c;
                 cs = fmaf(silent, c, cs);
             }
-            f_lo[tid] = len ? lo : 0;
-            f_len[tid] = keep;
-            f_off[tid] = off < 512 ? off : 0;
             f_csum[tid] = cs;
+            // smallest run length for which the bands need no more than 64 tasks
+            int run = 8, ntask = 0, base = 0;
+            for (;; ++run) {
+                ntask = (len + run - 1) / run;
+                int tot = ntask;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, tot, o);
+                    if (lane >= o) tot += v;
+                }
+                base = tot - ntask;
+                if (__shfl_sync(0xffffffffu, tot, 31) <= 64) break;
+            }
+            f_tb0[tid] = base;
+            f_tbn[tid] = ntask;
+            for (int i = 0; i < ntask; ++i) {
+                f_tk[base + i] = lo + i * run;
+                f_tn[base + i] = (len - i * run) < run ? (len - i * run) : run;
+                f_tc[base + i] = off + i * run;
+            }
+            const int total = __shfl_sync(0xffffffffu, base + ntask, 31);
+            for (int i = total + tid; i < 64; i += 32) {
+                f_tk[i] = 0;
+                f_tn[i] = 0;
+                f_tc[i] = 0;
+            }
         }
     }
     TwiddleRegs twr;
@@ -733,8 +767,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
 #pragma unroll
             for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
             __syncwarp();
+            // (the far-end tile of this half-warp is dead as well: it takes the magnitudes)
+            float* me = mag_e(hw);
             if (live) {
-                float* me = f_magE + hw * kMagPitch;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int k = h + 16 * q;
@@ -756,24 +791,45 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         }
         __syncthreads();
         {
-            const int j = tid >> 1, fp = tid & 1;
-            const int lo = f_lo[j], len = f_len[j];
-            const float* c = f_cb + f_off[j];
-            const float* mx0 = f_magX + (2 * fp) * kMagPitch + lo;
-            const float* mx1 = mx0 + kMagPitch;
-            const float* me0 = f_magE + (2 * fp) * kMagPitch + lo;
-            const float* me1 = me0 + kMagPitch;
-            float ax0 = 0.f, ax1 = 0.f, ae0 = 0.f, ae1 = 0.f;
-            for (int i = 0; i < len; ++i) {                            // ERB.py:282-283, ascending bins
+            // one task per thread: a run of one band's bins for the four far-end and the four error frames of the chunk
+            const int k0 = f_tk[tid], n = f_tn[tid];
+            const float* c = f_cb + f_tc[tid];
+            float ax[F], ae[F];
+#pragma unroll
+            for (int r = 0; r < F; ++r) {
+                ax[r] = 0.f;
+                ae[r] = 0.f;
+            }
+            for (int i = 0; i < n; ++i) {                              // ERB.py:282-283
                 const float cc = c[i];
-                ax0 = fmaf(mx0[i], cc, ax0);
-                ax1 = fmaf(mx1[i], cc, ax1);
-                ae0 = fmaf(me0[i], cc, ae0);
-                ae1 = fmaf(me1[i], cc, ae1);
+#pragma unroll
+                for (int r = 0; r < F; ++r) {
+                    ax[r] = fmaf(f_magX[r * kMagPitch + k0 + i], cc, ax[r]);
+                    ae[r] = fmaf(mag_e(r)[k0 + i], cc, ae[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < F; ++r) {
+                f_part[tid * 8 + r] = ax[r];
+                f_part[tid * 8 + F + r] = ae[r];
+            }
+        }
+        __syncthreads();
+        {
+            // lane pair (2j, 2j+1) finishes band j: the band's tasks in ascending order, two frames per lane
+            const int j = tid >> 1, fp = tid & 1;
+            const int b0 = f_tb0[j], bn = f_tbn[j];
+            float ax0 = 0.f, ax1 = 0.f, ae0 = 0.f, ae1 = 0.f;
+            for (int i = 0; i < bn; ++i) {
+                const float* pp = f_part + (b0 + i) * 8 + 2 * fp;
+                ax0 += pp[0];
+                ax1 += pp[1];
+                ae0 += pp[F];
+                ae1 += pp[F + 1];
             }
             const int tx = t0 + 2 * fp;                                // far-end frames of this chunk
-            if (tx < T) f_xerb[(tx & 7) * 32 + j] = ax0;
-            if (tx + 1 < T) f_xerb[((tx + 1) & 7) * 32 + j] = ax1;
+            if (tx < T) f_xerb[(tx % (F + 1)) * 32 + j] = ax0;
+            if (tx + 1 < T) f_xerb[((tx + 1) % (F + 1)) * 32 + j] = ax1;
             __syncwarp();                                              // the pair partner's far-end energies
             float* fb = prm.feat + (static_cast<long long>(blockIdx.x) * prm.feat_frames) * 64;
 #pragma unroll
@@ -781,7 +837,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                 const int tau = t0 - 1 + 2 * fp + r;
                 if (tau >= 0 && tau <= T - 1 && tau < prm.feat_frames) {
                     const float e = r ? ae1 : ae0;
-                    const float xe = f_xerb[(tau & 7) * 32 + j];
+                    const float xe = f_xerb[(tau % (F + 1)) * 32 + j];
                     fb[static_cast<long long>(tau) * 64 + j] = e;
                     fb[static_cast<long long>(tau) * 64 + 32 + j] = fabsf(e - xe);   // ERB.py:287-290
                 }

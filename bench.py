@@ -342,18 +342,67 @@ def roofline_of(wl, kern_ms, fp32_peak, hbm_peak, hbm_src, traffic=None):
             "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}}
 
 
+def fused_row(A, torch, wl, far, mic, err, cfg, args, fp32_peak, local):
+    """stage 1 + Stage-2 front end in one launch, against the two-launch pipeline on the same inputs (device-timed)"""
+    erb = torch.from_numpy(A.erb_filterbank()).float().cuda()
+    steps = max(5, min(args.steps, 20))
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        A.launch_count(reset=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps, A.launch_count()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.1)
+    w0 = time.perf_counter()
+    fused_ms, launches = timed(lambda: A.stage1_aec_features(far, mic, erb, cfg, out=err))
+    two_ms, _ = timed(lambda: (A.stage1_aec(far, mic, cfg, out=err), A.stage2_features(err, far, erb, in_norm=False)))
+    while time.perf_counter() - w0 < 0.35:
+        A.stage1_aec_features(far, mic, erb, cfg, out=err)
+        torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    time.sleep(0.05)
+    sampler.stop()
+    _, feat = A.stage1_aec_features(far, mic, erb, cfg, out=err)
+    want = A.stage2_features(err, far, erb, in_norm=False)
+    B, L = far.shape
+    return {"workload": wl["name"], "ms_per_step": fused_ms, "steps": steps,
+            "value": B * L / wl["sr"] / (fused_ms * 1e-3), "unit": "audio-s/s",
+            "two_launch_pipeline_ms": two_ms, "speedup_vs_two_launches": two_ms / fused_ms,
+            "features_max_abs_diff_vs_standalone": float((feat - want).abs().max()), "features_scale": float(want.abs().max()),
+            "hbm_bytes_algorithmic": {"fused": 3 * 4 * B * L + 4 * feat.numel(), "two_launches": 5 * 4 * B * L + 4 * feat.numel()},
+            "gpu_launches": int(launches), "outputs_finite": bool(torch.isfinite(feat).all()),
+            "clocks": sampler.summary(w0, w1, w0, w1)}
+
+
 def also_rows(A, torch, sharding, args, fp32_peak, hbm_peak, hbm_src, local):
     """Outside the headline's timed region (N = 1 only): the other single-GPU configurations of BASELINE.json and
     the many-wave batch, device-timed with the same method, so that they exist in the driver's record."""
     rows = []
     extra = [dict(WORKLOADS[3]), dict(WORKLOADS[4]),
-             dict(WORKLOADS[2], B=4144, name="many waves: 4144 x 10 s utterances (28 per SM), 16 kHz, 4-partition FDAF-NLMS")]
+             dict(WORKLOADS[2], B=4144, name="many waves: 4144 x 10 s utterances (28 per SM), 16 kHz, 4-partition FDAF-NLMS"),
+             dict(WORKLOADS[2], feat=True, name="configs[1] with the Stage-2 feature front end fused into the kernel "
+                                                "(aec_stage1_run_features: error signal + [B, T, 64] features per launch)")]
     for wl in extra:
         try:
             far, mic = make_inputs(torch, wl["B"], wl["L"], 7, wl["P"], wl["sr"], wl["frame"] // 2, device="cuda",
                                    draws="device")
             err = torch.empty_like(far)
             cfg = A.Stage1Config(frame=wl["frame"], partitions=wl["P"], algo=wl["algo"], erle_skip_hops=125)
+            if wl.get("feat"):
+                rows.append(fused_row(A, torch, wl, far, mic, err, cfg, args, fp32_peak, local))
+                del far, mic, err
+                torch.cuda.empty_cache()
+                continue
             for _ in range(3):
                 A.stage1_aec(far, mic, cfg, out=err, return_erle=True)
             torch.cuda.synchronize()
