@@ -74,6 +74,8 @@ SIGNATURES = {
     "aec_host_ctx_create": (C.c_int, [C.POINTER(_P), _I64, _I64]),
     "aec_host_ctx_create_ex": (C.c_int, [C.POINTER(_P), _I64, _I64, _I32, _I32]),
     "aec_host_ctx_destroy": (C.c_int, [_P]),
+    "aec_host_ctx_set_deferred": (C.c_int, [_P, _I32]),
+    "aec_host_ctx_wait": (C.c_int, [_P]),
     "aec_stage1_run_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, C.POINTER(AecCfg)]),
     "aec_stage1_run_host_pcm16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, C.POINTER(AecCfg)]),
     "aec_host_alloc": (C.c_int, [C.POINTER(_P), _I64]),

@@ -430,6 +430,8 @@ struct aec_host_ctx {
     long long* h_n[kMaxSlots] = {};
     int64_t pending_off[kMaxSlots];    // slice whose ERLE still sits in h_erle[k] (-1: none)
     int64_t pending_nb[kMaxSlots] = {};
+    float* pending_dst[kMaxSlots] = {}; // ... and the caller's erle_db array it belongs to (calls may overlap: deferred mode)
+    int deferred = 0;                  // 1: a run call returns without waiting for its last slices (aec_host_ctx_wait does)
     aec_host_ctx() {
         for (int i = 0; i < kMaxSlots; ++i) pending_off[i] = -1;
     }
@@ -449,12 +451,13 @@ static int64_t host_slice(const aec_host_ctx* ctx, int64_t done, int64_t remaini
     return (remaining + 1) / 2;
 }
 
-// drain slot k: wait for its stream, hand the staged ERLE values to the caller
-static int host_ctx_drain(aec_host_ctx* ctx, int k, float* erle_db) {
+// drain slot k: wait for its stream, hand the staged ERLE values to the caller (of the call that produced them)
+static int host_ctx_drain(aec_host_ctx* ctx, int k) {
     const cudaError_t e = cudaStreamSynchronize(ctx->stream[k]);
-    if (e == cudaSuccess && erle_db && ctx->pending_off[k] >= 0)
-        memcpy(erle_db + ctx->pending_off[k], ctx->h_erle[k], (size_t)ctx->pending_nb[k] * sizeof(float));
+    if (e == cudaSuccess && ctx->pending_dst[k] && ctx->pending_off[k] >= 0)
+        memcpy(ctx->pending_dst[k] + ctx->pending_off[k], ctx->h_erle[k], (size_t)ctx->pending_nb[k] * sizeof(float));
     ctx->pending_off[k] = -1;
+    ctx->pending_dst[k] = nullptr;
     if (e != cudaSuccess) {
         set_cuda_error(e, "aec_stage1_run_host: cudaStreamSynchronize");
         return AEC_ECUDA;
@@ -468,6 +471,7 @@ static void host_ctx_quiesce(aec_host_ctx* ctx) {
     for (int i = 0; i < ctx->slots; ++i) {
         if (ctx->stream[i]) (void)cudaStreamSynchronize(ctx->stream[i]);
         ctx->pending_off[i] = -1;
+        ctx->pending_dst[i] = nullptr;
     }
     (void)cudaGetLastError();
 }
@@ -527,6 +531,27 @@ extern "C" int aec_host_ctx_create_ex(aec_host_ctx** out, int64_t slice_utteranc
     return AEC_OK;
 }
 
+extern "C" int aec_host_ctx_wait(aec_host_ctx* ctx) {
+    if (!ctx) return AEC_EINVAL;
+    int rc = AEC_OK;
+    for (int i = 0; i < ctx->slots; ++i) {
+        const int r = host_ctx_drain(ctx, i);
+        if (r != AEC_OK && rc == AEC_OK) rc = r;
+    }
+    if (rc != AEC_OK) {
+        host_ctx_quiesce(ctx);
+        return rc;
+    }
+    AEC_CUDA_CHECK(cudaGetLastError());
+    return AEC_OK;
+}
+
+extern "C" int aec_host_ctx_set_deferred(aec_host_ctx* ctx, int32_t deferred) {
+    if (!ctx) return AEC_EINVAL;
+    ctx->deferred = deferred ? 1 : 0;
+    return AEC_OK;
+}
+
 extern "C" int aec_host_ctx_create(aec_host_ctx** out, int64_t slice_utterances, int64_t max_samples) {
     return aec_host_ctx_create_ex(out, slice_utterances, max_samples, 0, 0);
 }
@@ -572,7 +597,7 @@ int run_host_impl(aec_host_ctx* ctx, const In* far, const In* mic, float* err, f
         const int k = (int)(it % ctx->slots);
         nb = host_slice(ctx, off, B - off);
         cudaStream_t s = ctx->stream[k];
-        rc = host_ctx_drain(ctx, k, erle_db);       // slot k's previous slice (`slots` slices ago) is done
+        rc = host_ctx_drain(ctx, k);                // slot k's previous slice (`slots` slices ago, maybe of the previous call) is done
         if (rc != AEC_OK) break;
         In* up_f = kPcm ? reinterpret_cast<In*>(ctx->d_pcm[k]) : reinterpret_cast<In*>(ctx->d_far[k]);
         In* up_m = kPcm ? reinterpret_cast<In*>(ctx->d_pcm[k]) + sig_elems : reinterpret_cast<In*>(ctx->d_mic[k]);
@@ -618,6 +643,7 @@ int run_host_impl(aec_host_ctx* ctx, const In* far, const In* mic, float* err, f
             ok(cudaMemcpyAsync(ctx->h_erle[k], ctx->d_erle[k], (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, s));
             ctx->pending_off[k] = off;
             ctx->pending_nb[k] = nb;
+            ctx->pending_dst[k] = erle_db;
         }
     }
     if (e != cudaSuccess) {
@@ -628,16 +654,8 @@ int run_host_impl(aec_host_ctx* ctx, const In* far, const In* mic, float* err, f
         host_ctx_quiesce(ctx);
         return rc;
     }
-    for (int i = 0; i < ctx->slots; ++i) {
-        const int r = host_ctx_drain(ctx, i, erle_db);
-        if (r != AEC_OK && rc == AEC_OK) rc = r;
-    }
-    if (rc != AEC_OK) {
-        host_ctx_quiesce(ctx);
-        return rc;
-    }
-    AEC_CUDA_CHECK(cudaGetLastError());
-    return AEC_OK;
+    if (ctx->deferred) return AEC_OK;               // the last slices land under the next call / aec_host_ctx_wait
+    return aec_host_ctx_wait(ctx);
 }
 }  // namespace
 

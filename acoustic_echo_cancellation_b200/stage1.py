@@ -219,9 +219,18 @@ class HostPipeline:
         except Exception:
             pass
 
+    def wait(self):
+        """Complete every deferred ``run(..., wait=False)`` call: their outputs are in host memory afterwards."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.aec_host_ctx_wait(self._ctx), "aec_host_ctx_wait")
+        self._keep = []
+
     def run(self, far: np.ndarray, mic: np.ndarray, cfg: Optional[Stage1Config] = None,
             n_samples: Optional[np.ndarray] = None, err: Optional[np.ndarray] = None,
-            echo: Optional[np.ndarray] = None, erle: Optional[np.ndarray] = None):
+            echo: Optional[np.ndarray] = None, erle: Optional[np.ndarray] = None, wait: bool = True):
+        """``wait=False`` (streaming, batch after batch): return once the last slice is enqueued, so that the tail of
+        this batch runs under the first uploads of the next; outputs are complete after ``wait()``.  Consecutive
+        deferred calls need different output arrays."""
         cfg = cfg or Stage1Config()
         pcm16 = far.dtype == np.int16
         item = 2 if pcm16 else 4
@@ -243,7 +252,10 @@ class HostPipeline:
             ns = np.ascontiguousarray(n_samples, dtype=np.int64)
         c = cfg.to_c()
         fn = self._lib.aec_stage1_run_host_pcm16 if pcm16 else self._lib.aec_stage1_run_host
+        if not wait:     # the arrays of a deferred call must outlive it
+            self._keep = getattr(self, "_keep", [])[-8:] + [(far, mic, err, echo, erle, ns)]
         with torch.cuda.device(self.device):
+            _lib.check(self._lib.aec_host_ctx_set_deferred(self._ctx, 0 if wait else 1), "aec_host_ctx_set_deferred")
             rc = fn(self._ctx, far.ctypes.data, mic.ctypes.data, err.ctypes.data,
                     echo.ctypes.data if echo is not None else None,
                     erle.ctypes.data if erle is not None else None,

@@ -131,6 +131,14 @@ enum { AEC_HOST_CTX_NO_RAMP = 1 };
 int aec_host_ctx_create_ex(aec_host_ctx** ctx, int64_t slice_utterances, int64_t max_samples, int32_t slots,
                            int32_t flags);
 int aec_host_ctx_destroy(aec_host_ctx* ctx);
+/* Streaming use (batch after batch through one context): with deferred = 1 a run call returns as soon as its last
+ * slice has been ENQUEUED, so that the tail of batch k (last kernel + download, ~1 ms) runs under the first uploads of
+ * batch k+1.  The outputs (and erle_db) of a deferred call are complete after aec_host_ctx_wait(ctx) -- or once the
+ * next call has returned, for slices whose slot it has reused; the caller keeps every buffer of a call alive and
+ * unread until then, and gives consecutive calls DIFFERENT output buffers.  deferred = 0 (default): every call
+ * returns with its outputs in host memory. */
+int aec_host_ctx_set_deferred(aec_host_ctx* ctx, int32_t deferred);
+int aec_host_ctx_wait(aec_host_ctx* ctx);
 int aec_stage1_run_host(aec_host_ctx* ctx, const float* far, const float* mic, float* err, float* echo_est,
                         float* erle_db, const int64_t* n_samples, int64_t B, int64_t L, int64_t in_stride,
                         int64_t out_stride, const aec_cfg* cfg);

@@ -275,6 +275,24 @@ def test_host_pipeline_geometry_does_not_change_the_result():
         assert np.array_equal(err, dev) and np.array_equal(erle, dev_erle), (slots, sl, ramp)
     with pytest.raises(A.AecError):
         A.HostPipeline(16, L, slots=9)
+    # streaming (deferred) mode: calls return before their last slices have landed; after wait() every batch is the
+    # device path's result, whatever was in flight when the next call started
+    pipe = A.HostPipeline(32, L, slots=4)
+    outs = [A.pinned_empty((B, L)) for _ in range(3)]
+    erles = [np.zeros(B, dtype=np.float32) for _ in range(3)]
+    hf2 = A.pinned_empty((B, L))
+    hf2[:] = far[::-1]
+    hm2 = A.pinned_empty((B, L))
+    hm2[:] = mic[::-1]
+    pipe.run(hf, hm, cfg, err=outs[0], erle=erles[0], wait=False)
+    pipe.run(hf2, hm2, cfg, err=outs[1], erle=erles[1], wait=False)
+    pipe.run(hf, hm, cfg, err=outs[2], erle=erles[2], wait=False)
+    pipe.wait()
+    assert np.array_equal(outs[0], dev) and np.array_equal(outs[2], dev) and np.array_equal(outs[1], dev[::-1])
+    assert np.array_equal(erles[0], dev_erle) and np.array_equal(erles[1], dev_erle[::-1]) and np.array_equal(erles[2], dev_erle)
+    e4 = pipe.run(hf, hm, cfg, erle=erles[0])                     # back to the synchronous form on the same context
+    assert np.array_equal(e4, dev)
+    pipe.close()
 
 
 def test_runner_buffers_are_page_locked_and_pageable_inputs_are_staged():

@@ -52,15 +52,19 @@ def main():
             obj["n_ranks"] = world
             print(json.dumps(obj), flush=True)
 
-    def timed(fn, active=True, reps=3):
+    def timed(fn, active=True, reps=3, finish=None):
         """max over ranks of the per-repetition time of fn (inactive ranks only take part in the barriers)"""
         if active:
             fn()
+            if finish:
+                finish()
         barrier()
         t0 = time.perf_counter()
         if active:
             for _ in range(reps):
                 fn()
+            if finish:
+                finish()
         torch.cuda.synchronize()
         dt = torch.tensor([(time.perf_counter() - t0) / reps if active else 0.0], device="cuda", dtype=torch.float64)
         if world > 1:
@@ -162,6 +166,11 @@ def main():
         row["pcm16_ms"], row["pcm16_audio_s_per_s_total"] = dt * 1e3, world * B * 10.0 / dt
         dt = timed(lambda: pipe.run(wf, wm, cfg, err=he))
         row["pcm16_wc_ms"], row["pcm16_wc_audio_s_per_s_total"] = dt * 1e3, world * B * 10.0 / dt
+        # streaming: steps issued back to back in deferred mode, one wait at the end (the tail of a step under the next ramp)
+        dt = timed(lambda: pipe.run(h16f, h16m, cfg, err=he, wait=False), reps=4, finish=pipe.wait)
+        row["pcm16_streaming_ms"], row["pcm16_streaming_audio_s_per_s_total"] = dt * 1e3, world * B * 10.0 / dt
+        dt = timed(lambda: pipe.run(hf, hm, cfg, err=he, wait=False), reps=4, finish=pipe.wait)
+        row["f32_streaming_ms"], row["f32_streaming_audio_s_per_s_total"] = dt * 1e3, world * B * 10.0 / dt
         emit(row)
         pipe.close()
     if world > 1:
