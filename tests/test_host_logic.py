@@ -261,6 +261,37 @@ def test_wav_probe_and_pcm16_fast_read(tmp_path):
     assert ingest.read_pcm16_batch([p], dst, 16000, 1) is None
 
 
+def test_wav_probe_handles_extra_chunks_and_extensible_headers(tmp_path):
+    """RIFF files in the wild: a LIST chunk (odd size -> pad byte) before `data`, WAVE_FORMAT_EXTENSIBLE with the PCM
+    sub-format, a data chunk size of 0xFFFFFFFF (streamed) -- Python and native probes must agree and read the samples"""
+    import struct
+
+    from acoustic_echo_cancellation_b200 import ingest
+
+    x = (np.random.default_rng(2).standard_normal(777) * 4000).astype(np.int16)
+    body = x.tobytes()
+    fmt_ext = struct.pack("<HHIIHHHHIH14s", 0xFFFE, 1, 16000, 32000, 2, 16, 22, 16, 4, 1,
+                          bytes.fromhex("000000001000800000aa00389b71"))
+    lst = b"LIST" + struct.pack("<I", 7) + b"INFOabc" + b"\0"                # odd-sized chunk + pad byte
+    p1 = str(tmp_path / "ext.wav")
+    with open(p1, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 4 + 8 + len(fmt_ext) + len(lst) + 8 + len(body)) + b"WAVE")
+        f.write(b"fmt " + struct.pack("<I", len(fmt_ext)) + fmt_ext + lst)
+        f.write(b"data" + struct.pack("<I", 0xFFFFFFFF) + body)
+    for info in (ingest.probe_wav(p1), ingest.probe_batch([p1], 1)[0]):
+        assert (info.rate, info.channels, info.bits, info.fmt, info.frames) == (16000, 1, 16, 1, 777)
+        assert info.fast(16000)
+    dst = np.zeros((1, 800), dtype=np.int16)
+    fr = ingest.read_pcm16_batch([p1], dst, 16000, 2)
+    assert fr.tolist() == [777] and np.array_equal(dst[0, :777], x) and (dst[0, 777:] == 0).all()
+    row = np.zeros(800, dtype=np.int16)
+    ingest.read_pcm16_into(p1, ingest.probe_wav(p1), row)
+    assert np.array_equal(row, dst[0])
+    # truncated on purpose: shorter row than the file -> the first row_samples samples, true length still reported
+    short = np.zeros((1, 100), dtype=np.int16)
+    assert ingest.read_pcm16_batch([p1], short, 16000, 1).tolist() == [777] and np.array_equal(short[0], x[:100])
+
+
 def _shard_worker(rank, world, port, folder, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
