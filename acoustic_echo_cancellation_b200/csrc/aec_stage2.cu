@@ -19,7 +19,11 @@ constexpr int kIn = 64;         // 2 * bands
 // otherwise leave SMs empty -- the recurrence streams ~400 shared-memory wavefronts per utterance per frame, and four
 // utterances on one SM pay them one after the other while other SMs sit idle
 
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+// gate non-linearities on the frame-to-frame chain of the recurrence: MUFU.EX2 + MUFU.RCP forms (a few ulp; the pinned
+// tolerance of the inference is 2e-4 relative) instead of the IEEE division and the branchy tanhf -- each of the three
+// sits on the critical path of every time step
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float tanhf_(float v) { return 1.f - __fdividef(2.f, __expf(2.f * v) + 1.f); }
 
 // One warp per utterance, lane j = hidden unit / band j, CH = 8 frames per chunk (round 2: only what depends on h stays
 // on the frame-to-frame chain):
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(kMaskWarps * 32) stage2_mask_kernel(const floa
                 }
                 const float r = sigmoidf_(gr[f] + ((ar[0] + ar[1]) + (ar[2] + ar[3])));
                 const float z = sigmoidf_(gz[f] + ((az[0] + az[1]) + (az[2] + az[3])));
-                const float n = tanhf(fmaf(r, (an[0] + an[1]) + (an[2] + an[3]), gn[f]));
+                const float n = tanhf_(fmaf(r, (an[0] + an[1]) + (an[2] + an[3]), gn[f]));
                 h = fmaf(z, h - n, n);                   // (1 - z) n + z h
                 hb[f * kH + lane] = h;
                 __syncwarp();                            // every lane has read hs before the next step overwrites it
