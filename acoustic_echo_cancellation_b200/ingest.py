@@ -215,6 +215,43 @@ class BatchDecoder:
         # [nb, lmax] view with the buffer's row pitch would not be contiguous; the host entry takes a stride
         return buf[:nb, :lmax]
 
+    def _decode_native(self, slot, far_paths, mic_paths, extra) -> Optional[DecodedBatch]:
+        """All-native form of the fast path: one probe call, one read call per signal (C++ threads, no GIL)."""
+        nb = len(far_paths)
+        infos = probe_batch(list(far_paths) + list(mic_paths), self.threads)
+        if not all(a.fast(self.sr) for a in infos):
+            return None
+        fi, mi = infos[:nb], infos[nb:]
+        n = np.array([a.frames for a in fi], dtype=np.int64)
+        lmax = int(max(int(n.max()), 1))
+        far = self._buffer(slot, "far", nb, lmax, np.int16)
+        mic = self._buffer(slot, "mic", nb, lmax, np.int16)
+        if read_pcm16_batch(far_paths, far, self.sr, self.threads) is None:
+            return None
+        if read_pcm16_batch(mic_paths, mic, self.sr, self.threads) is None:
+            return None
+        signals: Dict[str, List[np.ndarray]] = {"__far__": [far[j, :n[j]] for j in range(nb)], "__mic__": []}
+        for j in range(nb):
+            if mi[j].frames > n[j]:
+                mic[j, n[j]:] = 0                       # the uploaded row follows the far-end clock
+            signals["__mic__"].append(mic[j, :n[j]] if mi[j].frames == n[j] else None)
+        ragged = [j for j in range(nb) if signals["__mic__"][j] is None]
+        for key, paths in list(extra.items()) + ([("__mic__", [mic_paths[j] for j in ragged])] if ragged else []):
+            ki = probe_batch(paths, self.threads)
+            if not all(a.fast(self.sr) for a in ki):
+                out = list(self.pool.map(lambda p: load_wav(p, self.sr), paths))
+            else:
+                cols = int(max([a.frames for a in ki] + [1]))
+                buf = self._buffer(slot, "store_" + key, len(paths), cols, np.int16, upload=False)
+                fr = read_pcm16_batch(paths, buf, self.sr, self.threads)
+                out = [buf[j, :fr[j]] for j in range(len(paths))]
+            if key == "__mic__":
+                for j, a in zip(ragged, out):
+                    signals["__mic__"][j] = a
+            else:
+                signals[key] = out
+        return DecodedBatch(far=far, mic=mic, n=n, pcm16=True, signals=signals)
+
     def decode(self, far_paths: Sequence[str], mic_paths: Sequence[str],
                extra: Dict[str, Sequence[str]]) -> DecodedBatch:
         """``extra`` maps a storage key (e.g. ``nearend_speech``) to its paths; those are decoded but only
@@ -282,47 +319,6 @@ class BatchDecoder:
         for key, paths in extra.items():
             signals[key] = list(self.pool.map(stored, paths))
         return DecodedBatch(far=far, mic=mic, n=n, pcm16=fast, signals=signals)
-
-
-def _decode_native(self, slot, far_paths, mic_paths, extra) -> Optional[DecodedBatch]:
-    """All-native form of the fast path: one probe call, one read call per signal (C++ threads, no GIL)."""
-    nb = len(far_paths)
-    infos = probe_batch(list(far_paths) + list(mic_paths), self.threads)
-    if not all(a.fast(self.sr) for a in infos):
-        return None
-    fi, mi = infos[:nb], infos[nb:]
-    n = np.array([a.frames for a in fi], dtype=np.int64)
-    lmax = int(max(int(n.max()), 1))
-    far = self._buffer(slot, "far", nb, lmax, np.int16)
-    mic = self._buffer(slot, "mic", nb, lmax, np.int16)
-    if read_pcm16_batch(far_paths, far, self.sr, self.threads) is None:
-        return None
-    if read_pcm16_batch(mic_paths, mic, self.sr, self.threads) is None:
-        return None
-    signals: Dict[str, List[np.ndarray]] = {"__far__": [far[j, :n[j]] for j in range(nb)], "__mic__": []}
-    for j in range(nb):
-        if mi[j].frames > n[j]:
-            mic[j, n[j]:] = 0                       # the uploaded row follows the far-end clock
-        signals["__mic__"].append(mic[j, :n[j]] if mi[j].frames == n[j] else None)
-    ragged = [j for j in range(nb) if signals["__mic__"][j] is None]
-    for key, paths in list(extra.items()) + ([("__mic__", [mic_paths[j] for j in ragged])] if ragged else []):
-        ki = probe_batch(paths, self.threads)
-        if not all(a.fast(self.sr) for a in ki):
-            out = list(self.pool.map(lambda p: load_wav(p, self.sr), paths))
-        else:
-            cols = int(max([a.frames for a in ki] + [1]))
-            buf = self._buffer(slot, "store_" + key, len(paths), cols, np.int16, upload=False)
-            fr = read_pcm16_batch(paths, buf, self.sr, self.threads)
-            out = [buf[j, :fr[j]] for j in range(len(paths))]
-        if key == "__mic__":
-            for j, a in zip(ragged, out):
-                signals["__mic__"][j] = a
-        else:
-            signals[key] = out
-    return DecodedBatch(far=far, mic=mic, n=n, pcm16=True, signals=signals)
-
-
-BatchDecoder._decode_native = _decode_native
 
 
 def as_float32(a: np.ndarray) -> np.ndarray:
