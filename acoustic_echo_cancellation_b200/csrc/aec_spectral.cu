@@ -201,7 +201,16 @@ __global__ void __launch_bounds__(kThreads) istft512_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------
 constexpr int kFeatMP = 259;   // magnitude row pitch (odd: lanes = frames read one bin conflict-free)
 
-__global__ void __launch_bounds__(kThreads) features512_kernel(const float* __restrict__ mic,
+// (round 2: the bank is no longer staged densely in shared memory -- 33 KB for 483 non-zeros --; the projection reads
+//  its coefficients through L1 (one broadcast load per bin, ~15 KB of sectors) and the output tile lives in the FFT
+//  tiles, which are dead by then: 51 KB per CTA instead of 88, four CTAs per SM instead of two.)
+__device__ __forceinline__ float sqrt_fast(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // 1 ulp; the arguments are >= 1e-9
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 4) features512_kernel(const float* __restrict__ mic,
                                                                const float* __restrict__ ref,
                                                                const float* __restrict__ erb, float* __restrict__ feat,
                                                                long long L, long long in_stride, long long T, int bands,
@@ -211,26 +220,23 @@ __global__ void __launch_bounds__(kThreads) features512_kernel(const float* __re
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tiles = reinterpret_cast<float2*>(smem);                                  // [8][kTilePitch]
     float* mag = reinterpret_cast<float*>(smem + 8 * kTilePitch * sizeof(float2));    // [2][kTT][kFeatMP]
-    float* erbs = mag + 2 * kTT * kFeatMP;                                            // [257][bands]
-    float* outt = erbs + kK * bands;                                                  // [kTT][2*bands]
-    int* lo = reinterpret_cast<int*>(outt + kTT * 2 * bands);                         // [bands]
+    int* lo = reinterpret_cast<int*>(mag + 2 * kTT * kFeatMP);                        // [bands]
     int* hi = lo + bands;                                                             // [bands]
+    float* outt = reinterpret_cast<float*>(tiles);                                    // [kTT][2*bands], aliases the (dead) tiles
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, h = lane & 15;
     const long long b = blockIdx.y;
     const long long n_tiles = (T + kTT - 1) / kTT;
 
-    for (int i = tid; i < bands; i += kThreads) {
-        lo[i] = kK;
-        hi[i] = 0;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < kK * bands; idx += kThreads) {
-        const float e = __ldg(erb + idx);
-        erbs[idx] = e;
-        if (e != 0.f) {
-            atomicMin(&lo[idx % bands], idx / bands);
-            atomicMax(&hi[idx % bands], idx / bands + 1);
-        }
+    // non-zero bin range of every band (the cosine bank is ~2 non-zeros per bin)
+    for (int j = tid; j < bands; j += kThreads) {
+        int l = kK, u = 0;
+        for (int k = 0; k < kK; ++k)
+            if (__ldg(erb + k * bands + j) != 0.f) {
+                l = l < k ? l : k;
+                u = k + 1;
+            }
+        lo[j] = l;
+        hi[j] = u;
     }
     const float* xb = (half == 0 ? mic : ref) + b * in_stride;
     // the batch-global scalar of ERB.py:254-255, by value or -- no host round trip -- from aec_batch_shift's output
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) features512_kernel(const float* __re
 
     for (long long tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x) {
         const long long t0 = tile_i * kTT;
-        __syncthreads();                       // previous tile's projection / copy-out finished
+        __syncthreads();                       // previous tile's projection / copy-out finished (and lo / hi visible)
         // ---- (1) analysis + magnitudes: warp w takes frames w, w+4, w+8, w+12 ----
         for (int i = 0; i < kTT / 4; ++i) {
             const int tt = warp + 4 * i;
@@ -257,13 +263,13 @@ __global__ void __launch_bounds__(kThreads) features512_kernel(const float* __re
                     xk.y = 0.f;
                     xm.y = 0.f;
                 }
-                mrow[k] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));        // ERB.py:277-278
-                mrow[256 - k] = sqrtf(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
+                mrow[k] = sqrt_fast(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));        // ERB.py:277-278
+                mrow[256 - k] = sqrt_fast(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
             }
             if (h == 0) {
                 float2 xk, xm;
                 unpack_pair_s(tile[128], tile[128], make_float2(0.f, -1.f), xk, xm);
-                mrow[128] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
+                mrow[128] = sqrt_fast(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
             }
             __syncwarp();
         }
@@ -273,8 +279,18 @@ __global__ void __launch_bounds__(kThreads) features512_kernel(const float* __re
             const float* mrow = mag + lane * kFeatMP;      // lane = half*16 + frame  ==  (sig*kTT + tt)
             for (int band = warp; band < bands; band += 4) {
                 const int k0 = lo[band], k1 = hi[band];
+                const float* cb = erb + band;
                 float acc = 0.f;
-                for (int k = k0; k < k1; ++k) acc = fmaf(mrow[k], erbs[k * bands + band], acc);   // ERB.py:282-283
+                int k = k0;
+                for (; k + 4 <= k1; k += 4) {                                              // ERB.py:282-283
+                    const float c0 = __ldg(cb + k * bands), c1 = __ldg(cb + (k + 1) * bands);
+                    const float c2 = __ldg(cb + (k + 2) * bands), c3 = __ldg(cb + (k + 3) * bands);
+                    acc = fmaf(mrow[k], c0, acc);
+                    acc = fmaf(mrow[k + 1], c1, acc);
+                    acc = fmaf(mrow[k + 2], c2, acc);
+                    acc = fmaf(mrow[k + 3], c3, acc);
+                }
+                for (; k < k1; ++k) acc = fmaf(mrow[k], __ldg(cb + k * bands), acc);
                 // mic projection in lanes 0-15, ref projection in lanes 16-31 of the same frame
                 const float other = __shfl_xor_sync(0xffffffffu, acc, 16);
                 if (half == 0) {
@@ -633,8 +649,8 @@ static int features_impl(const float* mic, const float* ref, const float* erb, f
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
     const long long T = aec_num_frames(L, frame);
+    // FFT tiles (reused for the [kTT][2*bands] output tile: 16 x 128 floats at most), magnitudes, band ranges
     const size_t smem = 8 * kTilePitch * sizeof(float2) + (size_t)2 * kTT * kFeatMP * sizeof(float) +
-                        (size_t)kK * bands * sizeof(float) + (size_t)kTT * 2 * bands * sizeof(float) +
                         (size_t)2 * bands * sizeof(int);
     rc = set_smem(features512_kernel, smem);
     if (rc != AEC_OK) return rc;

@@ -144,6 +144,12 @@ __device__ __forceinline__ void st_stream_f1(float* p, float v) {
 
 // MUFU.RCP without the range fix-up code of __fdividef / the Newton step of 1.0f / x (the argument
 // is a regularised power, far from the denormal / overflow ranges; 1 ulp is ample for 1e-4 parity)
+// MUFU.SQRT (1 ulp) for the magnitudes of the fused feature epilogue (arguments >= 1e-9; same form as aec_features)
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float rcp_fast(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -779,13 +785,13 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                         xk.y = 0.f;
                         xm.y = 0.f;
                     }
-                    me[k] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));        // ERB.py:277-278
-                    me[256 - k] = sqrtf(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
+                    me[k] = sqrt_approx(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));        // ERB.py:277-278
+                    me[256 - k] = sqrt_approx(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
                 }
                 if (h == 0) {
                     float2 xk, xm;
                     unpack_pair(tile[128], tile[128], make_float2(0.f, -1.f), xk, xm);
-                    me[128] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
+                    me[128] = sqrt_approx(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
                 }
             }
         }
@@ -949,8 +955,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     unpack_pair(zm[k], zm[km], wk[i], yk, ym);
                     if constexpr (FEAT) {                 // |X| for the far-end band energies (bins k and 256 - k)
                         float* mx = f_magX + tl * kMagPitch;
-                        mx[k] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
-                        mx[256 - k] = sqrtf(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
+                        mx[k] = sqrt_approx(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
+                        mx[256 - k] = sqrt_approx(fmaf(xm.x, xm.x, fmaf(xm.y, xm.y, 1e-9f)));
                     }
                     bin_step<P, ALGO>(st[2 * i], xk, yk, prm, ek, hk);
                     bin_step<P, ALGO>(st[2 * i + 1], xm, ym, prm, em, hm);
@@ -973,7 +979,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                         const float2 fa = zf[128], ma = zm[128];
                         unpack_pair(fa, fa, w_mid, xk, xm);
                         unpack_pair(ma, ma, w_mid, yk, ym);
-                        if constexpr (FEAT) f_magX[tl * kMagPitch + 128] = sqrtf(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
+                        if constexpr (FEAT) f_magX[tl * kMagPitch + 128] = sqrt_approx(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
                         BinState<P, ALGO> st_mid;
                         st_mid.load(mid_state);
                         bin_step<P, ALGO>(st_mid, xk, yk, prm, ek, hk);
