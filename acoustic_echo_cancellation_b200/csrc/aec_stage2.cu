@@ -207,114 +207,119 @@ __device__ __forceinline__ void pack_pair_2(float2 ek, float2 em, float2 w, floa
     gm = make_float2(a.x + t.y, t.x - a.y);
 }
 
-__global__ void __launch_bounds__(kThreads) stage2_synth_kernel(const float* __restrict__ mic,
-                                                                const float* __restrict__ est,
-                                                                const float* __restrict__ erb, float* __restrict__ y,
-                                                                long long L, long long in_stride, long long out_stride,
-                                                                long long T, float shift_val,
-                                                                const float* __restrict__ shift_dev, Tables tab) {
+// (round 2: the dense bank is no longer staged in shared memory -- 33 KB per CTA for ~2 non-zeros per bin, re-staged by
+//  every CTA for a single 15-hop tile --; a CTA now walks several tiles, reads the two or three coefficients of a bin
+//  through L1, and needs 54 KB instead of 87: four CTAs per SM instead of two.)
+__global__ void __launch_bounds__(kThreads, 4) stage2_synth_kernel(const float* __restrict__ mic,
+                                                                   const float* __restrict__ est,
+                                                                   const float* __restrict__ erb, float* __restrict__ y,
+                                                                   long long L, long long in_stride, long long out_stride,
+                                                                   long long T, float shift_val,
+                                                                   const float* __restrict__ shift_dev, Tables tab) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tiles = reinterpret_cast<float2*>(smem);                                   // [8][kTilePitch]
     float2* fr = tiles + 8 * kTilePitch;                                               // [kTT][256]
-    float* erbs = reinterpret_cast<float*>(fr + kTT * 256);                            // [257][32]
-    float* es = erbs + kK * kH;                                                        // [kTT][32]
+    float* es = reinterpret_cast<float*>(fr + kTT * 256);                              // [kTT][32]
     int* blo = reinterpret_cast<int*>(es + kTT * kH);                                  // [257]
     int* bhi = blo + kK;                                                               // [257]
     const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
-    const long long b = blockIdx.y, g0 = (long long)blockIdx.x * (kTT - 1);
+    const long long b = blockIdx.y;
     const float shift = shift_dev ? __ldg(shift_dev) : shift_val;      // ERB.py:254, by value or from aec_batch_shift
-    for (int i = tid; i < kK * kH; i += kThreads) erbs[i] = __ldg(erb + i);
-    for (int i = tid; i < kTT * kH; i += kThreads) {
-        const long long t = g0 + i / kH;
-        es[i] = t < T ? __ldg(est + (b * T + t) * kH + (i % kH)) : 0.f;
-    }
-    __syncthreads();
     for (int k = tid; k < kK; k += kThreads) {     // non-zero band range of bin k (the bank is ~2 bands per bin)
         int lo = kH, hi = 0;
         for (int j = 0; j < kH; ++j)
-            if (erbs[k * kH + j] != 0.f) {
+            if (__ldg(erb + k * kH + j) != 0.f) {
                 lo = min(lo, j);
                 hi = j + 1;
             }
         blo[k] = lo;
         bhi[k] = hi;
     }
-    __syncthreads();
     const float* xb = mic + b * in_stride;
+    float* yb = y + b * out_stride;
     float2* tile = tiles + hw * kTilePitch;
     auto gain = [&](int tt, int k) {               // ERB.py:306-307: (mask * mic_erb) @ erb^T
         float g = 0.f;
-        for (int j = blo[k]; j < bhi[k]; ++j) g = fmaf(es[tt * kH + j], erbs[k * kH + j], g);
+        for (int j = blo[k]; j < bhi[k]; ++j) g = fmaf(es[tt * kH + j], __ldg(erb + k * kH + j), g);
         return g;
     };
-    for (int i = 0; i < 2; ++i) {
-        const int tt = hw + 8 * i;
-        const long long t = g0 + tt;
-        // ---- analysis of the (shifted) microphone frame ----
-        {
-            float2 v[16];
-            const long long base = (t - 1) * 256;
-            const long long Lv = t < T ? L : 0;
+    const long long n_tiles = (T - 1 + kTT - 2) / (kTT - 1);
+    for (long long tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x) {
+        const long long g0 = tile_i * (kTT - 1);
+        __syncthreads();                           // previous tile's overlap-add finished (and blo / bhi visible)
+        for (int i = tid; i < kTT * kH; i += kThreads) {
+            const long long t = g0 + i / kH;
+            es[i] = t < T ? __ldg(est + (b * T + t) * kH + (i % kH)) : 0.f;
+        }
+        __syncthreads();
+        for (int i = 0; i < 2; ++i) {
+            const int tt = hw + 8 * i;
+            const long long t = g0 + tt;
+            // ---- analysis of the (shifted) microphone frame ----
+            {
+                float2 v[16];
+                const long long base = (t - 1) * 256;
+                const long long Lv = t < T ? L : 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const long long s = base + 2 * h + 32 * j;
-                const float2 wv = __ldg(&tab.win_a[h + 16 * j]);
-                const float x0 = (s >= 0 && s < Lv) ? __ldg(xb + s) - shift : 0.f;
-                const float x1 = (s + 1 >= 0 && s + 1 < Lv) ? __ldg(xb + s + 1) - shift : 0.f;
-                v[j] = make_float2(x0 * wv.x, x1 * wv.y);
+                for (int j = 0; j < 16; ++j) {
+                    const long long s = base + 2 * h + 32 * j;
+                    const float2 wv = __ldg(&tab.win_a[h + 16 * j]);
+                    const float x0 = (s >= 0 && s < Lv) ? __ldg(xb + s) - shift : 0.f;
+                    const float x1 = (s + 1 >= 0 && s + 1 < Lv) ? __ldg(xb + s + 1) - shift : 0.f;
+                    v[j] = make_float2(x0 * wv.x, x1 * wv.y);
+                }
+                __syncwarp();
+                fft256_halfwarp<false>(v, tile, tab.tw256, h);
+#pragma unroll
+                for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
+                __syncwarp();
+            }
+            // ---- per-bin gain, repack for the inverse transform (in place) ----
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = h + 16 * q, km = (256 - k) & 255;
+                const float2 wk = __ldg(&tab.tw512[k]);
+                float2 xk, xm, gk, gm;
+                unpack_pair_2(tile[k], tile[km], wk, xk, xm);
+                const float ga = gain(tt, k), gb = gain(tt, 256 - k);
+                xk = make_float2(ga * xk.x, k == 0 ? 0.f : ga * xk.y);       // ERB.py:309-310
+                xm = make_float2(gb * xm.x, k == 0 ? 0.f : gb * xm.y);
+                pack_pair_2(xk, xm, wk, gk, gm);
+                tile[k] = gk;
+                tile[km] = gm;
+            }
+            if (h == 0) {
+                float2 xk, xm, gk, gm;
+                unpack_pair_2(tile[128], tile[128], make_float2(0.f, -1.f), xk, xm);
+                const float ga = gain(tt, 128);
+                xk = make_float2(ga * xk.x, ga * xk.y);
+                pack_pair_2(xk, xk, make_float2(0.f, -1.f), gk, gm);
+                tile[128] = gk;
             }
             __syncwarp();
-            fft256_halfwarp<false>(v, tile, tab.tw256, h);
+            float2 v[16];
 #pragma unroll
-            for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
+            for (int j = 0; j < 16; ++j) v[j] = tile[h + 16 * j];
+            __syncwarp();
+            fft256_halfwarp<true>(v, tile, tab.tw256, h);
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int r = fft16_index(p);
+                const float2 wv = __ldg(&tab.win_s[h + 16 * r]);
+                fr[tt * 256 + h + 16 * r] = make_float2(v[p].x * wv.x, v[p].y * wv.y);
+            }
             __syncwarp();
         }
-        // ---- per-bin gain, repack for the inverse transform (in place) ----
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int k = h + 16 * q, km = (256 - k) & 255;
-            const float2 wk = __ldg(&tab.tw512[k]);
-            float2 xk, xm, gk, gm;
-            unpack_pair_2(tile[k], tile[km], wk, xk, xm);
-            const float ga = gain(tt, k), gb = gain(tt, 256 - k);
-            xk = make_float2(ga * xk.x, k == 0 ? 0.f : ga * xk.y);       // ERB.py:309-310
-            xm = make_float2(gb * xm.x, k == 0 ? 0.f : gb * xm.y);
-            pack_pair_2(xk, xm, wk, gk, gm);
-            tile[k] = gk;
-            tile[km] = gm;
-        }
-        if (h == 0) {
-            float2 xk, xm, gk, gm;
-            unpack_pair_2(tile[128], tile[128], make_float2(0.f, -1.f), xk, xm);
-            const float ga = gain(tt, 128);
-            xk = make_float2(ga * xk.x, ga * xk.y);
-            pack_pair_2(xk, xk, make_float2(0.f, -1.f), gk, gm);
-            tile[128] = gk;
-        }
-        __syncwarp();
-        float2 v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = tile[h + 16 * j];
-        __syncwarp();
-        fft256_halfwarp<true>(v, tile, tab.tw256, h);
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            const int r = fft16_index(p);
-            const float2 wv = __ldg(&tab.win_s[h + 16 * r]);
-            fr[tt * 256 + h + 16 * r] = make_float2(v[p].x * wv.x, v[p].y * wv.y);
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    float* yb = y + b * out_stride;
-    for (int idx = tid; idx < (kTT - 1) * 128; idx += kThreads) {
-        const int tt = idx / 128, m = idx % 128;
-        const long long g = g0 + tt;
-        if (g + 1 <= T - 1) {
-            const float2 a = fr[tt * 256 + 128 + m];
-            const float2 c = fr[(tt + 1) * 256 + m];
-            yb[g * 256 + 2 * m] = a.x + c.x + 1e-9f;                     // ERB.py:316
-            yb[g * 256 + 2 * m + 1] = a.y + c.y + 1e-9f;
+        __syncthreads();
+        for (int idx = tid; idx < (kTT - 1) * 128; idx += kThreads) {
+            const int tt = idx / 128, m = idx % 128;
+            const long long g = g0 + tt;
+            if (g + 1 <= T - 1) {
+                const float2 a = fr[tt * 256 + 128 + m];
+                const float2 c = fr[(tt + 1) * 256 + m];
+                yb[g * 256 + 2 * m] = a.x + c.x + 1e-9f;                     // ERB.py:316
+                yb[g * 256 + 2 * m + 1] = a.y + c.y + 1e-9f;
+            }
         }
     }
 }
@@ -374,10 +379,16 @@ static int synth_impl(const float* mic, const float* est_erb, const float* erb, 
     Tables tab;
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
-    const size_t smem = (size_t)(8 * kTilePitch + kTT * 256) * sizeof(float2) + (size_t)(kK * kH + kTT * kH) * sizeof(float) +
+    const size_t smem = (size_t)(8 * kTilePitch + kTT * 256) * sizeof(float2) + (size_t)(kTT * kH) * sizeof(float) +
                         (size_t)2 * kK * sizeof(int);
     AEC_CUDA_CHECK(cudaFuncSetAttribute(stage2_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((T - 1 + kTT - 2) / (kTT - 1)), (unsigned)B);
+    // a CTA walks several tiles of one utterance, so that the per-CTA set-up (band ranges) is not paid per tile
+    const long long n_tiles = (T - 1 + kTT - 2) / (kTT - 1);
+    long long per_utt = n_tiles;
+    if (B >= 512) per_utt = 2; else if (B >= 64) per_utt = 8;
+    if (per_utt > n_tiles) per_utt = n_tiles;
+    if (per_utt < 1) per_utt = 1;
+    dim3 grid((unsigned)per_utt, (unsigned)B);
     stage2_synth_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
         mic, est_erb, erb, out, L, in_stride, out_stride, T, shift_mic, shift_mic_dev, tab);
     AEC_CUDA_CHECK(cudaGetLastError());
