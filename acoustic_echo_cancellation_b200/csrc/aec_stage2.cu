@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kMaskWarps * 32) stage2_mask_kernel(const floa
 
 // ---- synthesis: out = iSTFT((est_erb @ erb^T) * STFT(mic - shift)) + 1e-9 -------------------
 constexpr int kTT = 16, kThreads = 128, kK = 257, kPitch = kTT + 1;
+static_assert(((8 * kTilePitch + kTT * 256) * 8 + kTT * kH * 4 + 2 * kK * 4) % 8 == 0, "coefficient pairs must be 8-byte aligned");
 
 __device__ __forceinline__ void unpack_pair_2(float2 fa, float2 fb, float2 w, float2& xk, float2& xm) {
     const float2 a = make_float2(fa.x + fb.x, fa.y - fb.y);
@@ -222,25 +223,32 @@ __global__ void __launch_bounds__(kThreads, 4) stage2_synth_kernel(const float* 
     float* es = reinterpret_cast<float*>(fr + kTT * 256);                              // [kTT][32]
     int* blo = reinterpret_cast<int*>(es + kTT * kH);                                  // [257]
     int* bhi = blo + kK;                                                               // [257]
+    float2* c2 = reinterpret_cast<float2*>(bhi + kK);                                  // [257]  (offset 54280: 8-byte aligned)
     const int tid = threadIdx.x, lane = tid & 31, hw = tid >> 4, h = lane & 15;
     const long long b = blockIdx.y;
     const float shift = shift_dev ? __ldg(shift_dev) : shift_val;      // ERB.py:254, by value or from aec_batch_shift
-    for (int k = tid; k < kK; k += kThreads) {     // non-zero band range of bin k (the bank is ~2 bands per bin)
+    for (int k = tid; k < kK; k += kThreads) {     // non-zero band range of bin k (the bank is <= 2 bands per bin)
         int lo = kH, hi = 0;
         for (int j = 0; j < kH; ++j)
             if (__ldg(erb + k * kH + j) != 0.f) {
                 lo = min(lo, j);
                 hi = j + 1;
             }
-        blo[k] = lo;
-        bhi[k] = hi;
+        blo[k] = lo < kH ? lo : 0;
+        bhi[k] = hi > lo ? hi : blo[k];
+        // the first two coefficients of the range stay in shared memory (all of them, for the reference's bank)
+        c2[k] = make_float2(lo < hi ? __ldg(erb + k * kH + lo) : 0.f, lo + 1 < hi ? __ldg(erb + k * kH + lo + 1) : 0.f);
     }
     const float* xb = mic + b * in_stride;
     float* yb = y + b * out_stride;
     float2* tile = tiles + hw * kTilePitch;
     auto gain = [&](int tt, int k) {               // ERB.py:306-307: (mask * mic_erb) @ erb^T
-        float g = 0.f;
-        for (int j = blo[k]; j < bhi[k]; ++j) g = fmaf(es[tt * kH + j], __ldg(erb + k * kH + j), g);
+        const int lo = blo[k], hi = bhi[k];
+        const float2 c = c2[k];
+        const float* e = es + tt * kH + lo;
+        float g = fmaf(e[0], c.x, 0.f);
+        g = fmaf(e[lo + 1 < kH ? 1 : 0], c.y, g);   // (c.y is zero when the range has one band)
+        for (int j = lo + 2; j < hi; ++j) g = fmaf(es[tt * kH + j], __ldg(erb + k * kH + j), g);   // wider banks only
         return g;
     };
     const long long n_tiles = (T - 1 + kTT - 2) / (kTT - 1);
@@ -260,13 +268,25 @@ __global__ void __launch_bounds__(kThreads, 4) stage2_synth_kernel(const float* 
                 float2 v[16];
                 const long long base = (t - 1) * 256;
                 const long long Lv = t < T ? L : 0;
+                // interior frames of 8-byte aligned rows: unpredicated 64-bit loads (the common case; the scalar
+                // predicated form made this kernel wait on global loads: long_scoreboard 7.8 per issue)
+                if (t >= 1 && base + 512 <= Lv && ((reinterpret_cast<uintptr_t>(xb) & 7) == 0)) {
+                    const float2* xp = reinterpret_cast<const float2*>(xb + base) + h;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const long long s = base + 2 * h + 32 * j;
-                    const float2 wv = __ldg(&tab.win_a[h + 16 * j]);
-                    const float x0 = (s >= 0 && s < Lv) ? __ldg(xb + s) - shift : 0.f;
-                    const float x1 = (s + 1 >= 0 && s + 1 < Lv) ? __ldg(xb + s + 1) - shift : 0.f;
-                    v[j] = make_float2(x0 * wv.x, x1 * wv.y);
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 wv = __ldg(&tab.win_a[h + 16 * j]);
+                        const float2 xv = __ldg(xp + 16 * j);
+                        v[j] = make_float2((xv.x - shift) * wv.x, (xv.y - shift) * wv.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const long long s = base + 2 * h + 32 * j;
+                        const float2 wv = __ldg(&tab.win_a[h + 16 * j]);
+                        const float x0 = (s >= 0 && s < Lv) ? __ldg(xb + s) - shift : 0.f;
+                        const float x1 = (s + 1 >= 0 && s + 1 < Lv) ? __ldg(xb + s + 1) - shift : 0.f;
+                        v[j] = make_float2(x0 * wv.x, x1 * wv.y);
+                    }
                 }
                 __syncwarp();
                 fft256_halfwarp<false>(v, tile, tab.tw256, h);
@@ -380,7 +400,7 @@ static int synth_impl(const float* mic, const float* est_erb, const float* erb, 
     int rc = get_tables(&tab);
     if (rc != AEC_OK) return rc;
     const size_t smem = (size_t)(8 * kTilePitch + kTT * 256) * sizeof(float2) + (size_t)(kTT * kH) * sizeof(float) +
-                        (size_t)2 * kK * sizeof(int);
+                        (size_t)(2 * kK) * sizeof(int) + (size_t)kK * sizeof(float2);
     AEC_CUDA_CHECK(cudaFuncSetAttribute(stage2_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // a CTA walks several tiles of one utterance, so that the per-CTA set-up (band ranges) is not paid per tile
     const long long n_tiles = (T - 1 + kTT - 2) / (kTT - 1);
