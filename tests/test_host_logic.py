@@ -304,6 +304,41 @@ def _shard_worker(rank, world, port, folder, ret):
     dist.destroy_process_group()
 
 
+def _gen_worker(rank, world, port, wav_dir, h5_dir, list_dir, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    args = types.SimpleNamespace(train_path=wav_dir, h5_path=h5_dir, list_path=list_dir, sr=16000)
+    st = {}
+    merged = wav2h5.create_h5(args, runner=_fake_runner, batch=2, h5=wav2h5.RawStore(), stats=st)
+    ret[rank] = (merged, st["utterances"])
+    dist.destroy_process_group()
+
+
+def test_two_rank_generation_writes_every_utterance_once(tmp_path):
+    """config 5 shape on two ranks (gloo): each rank converts its shard of the sorted id list, the union is the corpus,
+    rank 0 writes the merged tr_list.txt, every listed file exists and holds its own utterance"""
+    wav_dir, h5_dir, list_dir = tmp_path / "wav", tmp_path / "h5", tmp_path / "lists"
+    for d in (wav_dir, h5_dir, list_dir):
+        d.mkdir()
+    ids = [str(i) for i in (5, 17, 2, 40, 8, 23, 11)]
+    data = _write_wavs(str(wav_dir), ids, n=700)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_gen_worker, args=(2, port, str(wav_dir), str(h5_dir), str(list_dir), ret), nprocs=2, join=True)
+    merged0, n0 = ret[0]
+    merged1, n1 = ret[1]
+    assert merged0 == merged1 and n0 + n1 == len(ids) and abs(n0 - n1) <= 1
+    assert [os.path.basename(p) for p in merged0] == [f"tr_{i}.ex" for i in sorted(ids, key=int)]
+    assert open(list_dir / "tr_list.txt").read().split("\n") == merged0
+    for p in merged0:
+        idx = os.path.basename(p)[3:-3]
+        z = wav2h5.RawStore.load(p)
+        assert np.array_equal(z["echo"], data[(idx, "echo")].astype(np.float32) / np.float32(32768))
+        assert np.array_equal(z["stage1_error"], np.float32(0.5) * z["farend_speech"])
+
+
 def test_two_rank_shards_are_disjoint_and_complete(tmp_path):
     ids = [str(i) for i in (12, 3, 100, 7, 45, 9, 1)]
     _write_wavs(str(tmp_path), ids, n=64)
