@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("AEC_B200_LIB") or os.path.join(_HERE, "libaec_b200.so
 
 ALGO_NLMS = 0
 ALGO_KALMAN = 1
+ALGO_PBFDAF = 2
 
 
 class AecCfg(C.Structure):
@@ -33,7 +34,8 @@ class AecCfg(C.Structure):
         ("erle_skip_hops", C.c_int32),
         ("variant", C.c_int32),
         ("stagger_ns", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("pb_lambda", C.c_float),
+        ("reserved", C.c_int32 * 3),
     ]
 
 

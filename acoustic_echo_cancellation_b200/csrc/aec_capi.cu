@@ -13,6 +13,7 @@
 #include "aec_common.cuh"
 #include "stage1_launch.cuh"
 #include "stage1_kernel_1024.cuh"
+#include "stage1_ols_kernel.cuh"
 
 namespace aec {
 
@@ -243,6 +244,7 @@ extern "C" int aec_cfg_default(aec_cfg* cfg, int32_t frame) {
     cfg->kalman_lambda = 0.9f;
     cfg->kalman_c0 = 1.0f;
     cfg->kalman_eps = 1e-10f;
+    cfg->pb_lambda = 0.5f;
     cfg->erle_skip_hops = 0;
     cfg->variant = 0;
     return AEC_OK;
@@ -275,7 +277,7 @@ static int validate_cfg(const aec_cfg* cfg) {
     if (!cfg) return AEC_EINVAL;
     if (cfg->frame != 512 && cfg->frame != 1024) return AEC_EUNSUPPORTED;
     if (cfg->partitions < 1) return AEC_EINVAL;
-    if (cfg->algo != AEC_ALGO_NLMS && cfg->algo != AEC_ALGO_KALMAN) return AEC_EINVAL;
+    if (cfg->algo != AEC_ALGO_NLMS && cfg->algo != AEC_ALGO_KALMAN && cfg->algo != AEC_ALGO_PBFDAF) return AEC_EINVAL;
     if (cfg->erle_skip_hops < 0) return AEC_EINVAL;
     return AEC_OK;
 }
@@ -324,6 +326,8 @@ static int stage1_run_impl(const float* far, const float* mic, float* err, float
     p.koml = 1.0f - cfg->kalman_lambda;
     p.kc0 = cfg->kalman_c0;
     p.keps = cfg->kalman_eps;
+    p.pblam = cfg->pb_lambda;
+    p.pboml = 1.0f - cfg->pb_lambda;
     p.erle_skip_hops = cfg->erle_skip_hops;
     p.feat = feat;
     p.erb = erb;
@@ -364,7 +368,10 @@ static int stage1_run_impl(const float* far, const float* mic, float* err, float
         //  128 registers for the two-warp kernels so that 7 utterances stay resident per SM)
     }
     cudaError_t e;
-    if (feat) {
+    if (cfg->algo == AEC_ALGO_PBFDAF) {
+        if (feat || wide) return AEC_EUNSUPPORTED;       // frame 512, no fused features for the overlap-save filter
+        e = launch_stage1_ols(P, echo, p, s);
+    } else if (feat) {
         e = launch_stage1_feat(P, cfg->algo, p, s);
     } else if (wide) {
         e = launch_stage1_1024(P, cfg->algo, echo, minb, p, s);

@@ -35,7 +35,7 @@
 
 namespace aec {
 
-enum { kAlgoNlms = 0, kAlgoKalman = 1 };
+enum { kAlgoNlms = 0, kAlgoKalman = 1, kAlgoPbfdaf = 2 };
 
 // "this (P, algo, echo, register cap) is not instantiated": a code no launch path of the runtime produces
 constexpr cudaError_t kNoInstance = cudaErrorStubLibrary;
@@ -50,6 +50,7 @@ struct Stage1Params {
     long long B, L, in_stride, out_stride;
     float mu, delta;                         // NLMS
     float ka, ka2, kq, klam, koml, kc0, keps;  // Kalman: A, A^2, 1-A^2, lambda, 1-lambda, c0, eps
+    float pblam, pboml;                        // overlap-save PBFDAF (algo 2): power smoothing lambda, 1 - lambda
     int erle_skip_hops;
     int use_tma;      // inputs 16-byte aligned per hop -> bulk copies
     int vec_out;      // outputs 8-byte aligned -> float2 stores

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ALGO_KALMAN, ALGO_NLMS  # noqa: F401  (re-exported)
+from ._lib import ALGO_KALMAN, ALGO_NLMS, ALGO_PBFDAF  # noqa: F401  (re-exported)
 
 
 @dataclass
@@ -35,6 +35,7 @@ class Stage1Config:
     kalman_lambda: float = 0.9
     kalman_c0: float = 1.0
     kalman_eps: float = 1e-10
+    pb_lambda: float = 0.5
     erle_skip_hops: int = 0
     variant: int = 0
     stagger_ns: int = 0
@@ -49,7 +50,7 @@ class Stage1Config:
             self.frame, partitions=self.partitions, algo=self.algo, mu=self.mu,
             delta=(1e-6 * self.frame if self.delta is None else self.delta),
             kalman_a=self.kalman_a, kalman_lambda=self.kalman_lambda, kalman_c0=self.kalman_c0,
-            kalman_eps=self.kalman_eps, erle_skip_hops=self.erle_skip_hops, variant=self.variant,
+            kalman_eps=self.kalman_eps, pb_lambda=self.pb_lambda, erle_skip_hops=self.erle_skip_hops, variant=self.variant,
             stagger_ns=self.stagger_ns)
 
 

@@ -43,7 +43,11 @@ enum {
     AEC_EIO = -6          /* a file could not be opened / read (wav ingest) */
 };
 
-enum { AEC_ALGO_NLMS = 0, AEC_ALGO_KALMAN = 1 };
+/* 0, 1: the STFT-domain recurrence (Hann-windowed STFT, one complex tap per bin and past hop) with an NLMS / Kalman step;
+ * 2: overlap-save partitioned-block FDAF with the alternated gradient constraint -- time-domain blocks of hop new
+ *    samples, FFT length frame, exact linear convolution (no analysis window; ~26 dB more ERLE on the single-talk set,
+ *    DESIGN.md section 2); NLMS step on a smoothed input power.  Frame 512, partitions 1 / 2 / 4. */
+enum { AEC_ALGO_NLMS = 0, AEC_ALGO_KALMAN = 1, AEC_ALGO_PBFDAF = 2 };
 
 /* Parameter block of the stage-1 filter.  frame / hop follow the reference's
  * speech_conf (Stage2_lhm/scripts/configs.py:1-8: win_size 512, hop_size 256) and the window is
@@ -61,7 +65,8 @@ typedef struct aec_cfg {
     int32_t erle_skip_hops; /* hops excluded from the ERLE sums at the start of each utterance */
     int32_t variant;        /* 0 = library default; otherwise 1000*warps_per_utterance + register cap */
     int32_t stagger_ns;     /* tuning: start-up skew (ns per resident slot) between co-resident utterances; <= 0 = off (default) */
-    int32_t reserved[4];
+    float pb_lambda;        /* algo 2: smoothing of the per-bin input power (default 0.5) */
+    int32_t reserved[3];
 } aec_cfg;
 
 int aec_version(void);

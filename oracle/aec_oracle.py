@@ -43,6 +43,7 @@ HOP_SIZE = 256
 
 ALGO_NLMS = 0
 ALGO_KALMAN = 1
+ALGO_PBFDAF = 2       # overlap-save constrained PBFDAF (round 2; time-domain blocks, no STFT framing)
 
 
 @dataclass(frozen=True)
@@ -58,6 +59,7 @@ class AecConfig:
     kalman_lambda: float = 0.9     # smoothing of the observation-noise estimate
     kalman_c0: float = 1.0         # initial state covariance
     kalman_eps: float = 1e-10      # keeps D > 0 on digital silence
+    pb_lambda: float = 0.5         # PBFDAF: smoothing of the per-bin input power
 
     @property
     def hop(self) -> int:
@@ -251,6 +253,54 @@ def fdaf_kalman(X: np.ndarray, Y: np.ndarray, cfg: AecConfig, dtype=np.float64):
     return E, Yh
 
 
+def pbfdaf_ols(far: np.ndarray, mic: np.ndarray, cfg: AecConfig, dtype=np.float64):
+    """Overlap-save partitioned-block FDAF with the alternated gradient constraint (algo = 2; BUILDER-AUTHORED,
+    parity unpinned like the other recurrences).  One utterance, time-domain in, time-domain out: blocks of
+    H = frame / 2 new samples, FFT length 2H = frame, P partitions -> the same P*H-sample tail as algos 0 / 1, but as
+    an exact linear convolution (no analysis window, no cross-band leakage).
+
+    per block t (W_p = 0, Xh_p = 0, Pw = 0, x_{-1} = 0 initially):
+        Xh_p   = Xh_{p-1} (shift);  Xh_0 = rfft([x_{t-1}, x_t])
+        y      = irfft(sum_p W_p Xh_p)[H:]           e = d_t - y            E = rfft([0_H, e])
+        Pw     = lam Pw + (1 - lam) sum_p |Xh_p|^2
+        W_p   += mu / (Pw + delta) * conj(Xh_p) * E
+        c = t mod P:   g = irfft(W_c);  g[H:] = 0;  W_c = rfft(g)          (one partition constrained per block)
+    Returns (err, yhat), each (n // H) * H samples."""
+    cd = _cdtype(dtype)
+    far = np.asarray(far, dtype=dtype)
+    mic = np.asarray(mic, dtype=dtype)
+    N, H, P = cfg.frame, cfg.hop, cfg.partitions
+    K = H + 1
+    nblk = min(len(far), len(mic)) // H
+    W = np.zeros((P, K), dtype=cd)
+    Xh = np.zeros((P, K), dtype=cd)
+    pw = np.zeros(K, dtype=dtype)
+    prev = np.zeros(H, dtype=dtype)
+    mu, delta, lam = dtype(cfg.mu), dtype(cfg.delta), dtype(cfg.pb_lambda)
+    one = dtype(1.0)
+    err = np.zeros(nblk * H, dtype=dtype)
+    yh = np.zeros(nblk * H, dtype=dtype)
+    zeros = np.zeros(H, dtype=dtype)
+    for t in range(nblk):
+        cur = far[t * H:(t + 1) * H]
+        Xh[1:] = Xh[:-1].copy()
+        Xh[0] = np.fft.rfft(np.concatenate([prev, cur])).astype(cd)
+        prev = cur
+        y = np.fft.irfft((W * Xh).sum(axis=0), n=N)[H:].astype(dtype)
+        e = mic[t * H:(t + 1) * H] - y
+        err[t * H:(t + 1) * H] = e
+        yh[t * H:(t + 1) * H] = y
+        E = np.fft.rfft(np.concatenate([zeros, e])).astype(cd)
+        pw = lam * pw + (one - lam) * (Xh.real ** 2 + Xh.imag ** 2).sum(axis=0).astype(dtype)
+        g = (mu / (pw + delta)).astype(dtype)
+        W = W + np.conj(Xh) * (g * E)[None, :]
+        c = t % P
+        gt = np.fft.irfft(W[c], n=N).astype(dtype)
+        gt[H:] = 0
+        W[c] = np.fft.rfft(gt).astype(cd)
+    return err, yh
+
+
 def erle_db(num_sig: np.ndarray, den_sig: np.ndarray, skip: int = 0) -> np.ndarray:
     """ERLE in dB per utterance over samples [skip:]: 10 log10(sum num^2 / sum den^2).
     Single-talk: num = mic, den = error.  Double-talk: num = echo, den = echo - echo_est.
@@ -286,6 +336,13 @@ def stage1(far: np.ndarray, mic: np.ndarray, cfg: AecConfig = AecConfig(),
     run = fdaf_nlms if cfg.algo == ALGO_NLMS else fdaf_kalman
     for b in range(B):
         n = int(n_samples[b])
+        if cfg.algo == ALGO_PBFDAF:             # time-domain blocks: (n // H) * H output samples, like (T - 1) * H
+            e, yh = pbfdaf_ols(far[b, :n], mic[b, :n], cfg, dtype)
+            err[b, :e.shape[0]] = e
+            echo[b, :yh.shape[0]] = yh
+            m = e.shape[0]
+            erle[b] = erle_db(mic[b, :m], e, erle_skip)[0] if m > erle_skip else 0.0
+            continue
         X = stft_complex(far[b:b + 1, :n], N, H, dtype)[0]
         Y = stft_complex(mic[b:b + 1, :n], N, H, dtype)[0]
         E, Yh = run(X, Y, cfg, dtype)

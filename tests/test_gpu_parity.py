@@ -420,6 +420,44 @@ def test_fused_feature_epilogue_ragged_rows_and_golden_front_end(golden):
     assert float((f - want).abs().max()) <= 2e-5 * max(float(want.abs().max()), 1.0)
 
 
+@pytest.mark.parametrize("P,L,B", [(4, 16000 + 123, 3), (2, 8 * 256, 2), (1, 4097, 2), (4, 300, 2), (4, 160000, 2)])
+def test_overlap_save_pbfdaf_matches_oracle(P, L, B):
+    """algo = 2 (overlap-save PBFDAF, alternated constraint; builder-authored, parity unpinned): error signal, echo
+    estimate and ERLE against the float64 numpy oracle; same tolerance as the STFT-domain recurrences"""
+    d = synth.make_batch(70, B, L, rir_len=min(P * 256, 1024))
+    ns = np.array(([L, max(L - 777, 1), 255] * B)[:B], dtype=np.int64) if L < 100000 else None
+    skip = 8
+    ref = O.stage1(d["far"], d["mic"], O.AecConfig(partitions=P, algo=O.ALGO_PBFDAF), n_samples=ns, erle_skip=skip * 256)
+    cfg = A.Stage1Config(partitions=P, algo=A.ALGO_PBFDAF, erle_skip_hops=skip)
+    err, echo, erle = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg, n_samples=None if ns is None else _cuda(ns),
+                                   return_echo=True, return_erle=True)
+    torch.cuda.synchronize()
+    err, echo, erle = err.cpu().numpy(), echo.cpu().numpy(), erle.cpu().numpy()
+    n = ref["err"].shape[1]
+    if n:
+        assert np.abs(err[:, :n] - ref["err"]).max() <= TOL_ERR
+        assert np.abs(echo[:, :n] - ref["echo"]).max() <= TOL_ERR
+    assert (err[:, n:] == 0).all() and (echo[:, n:] == 0).all()
+    lens = ns if ns is not None else [L] * B
+    for b in range(B):
+        m = (int(lens[b]) // 256) * 256
+        assert (err[b, m:] == 0).all()
+        if m > skip * 256:
+            assert abs(erle[b] - ref["erle_db"][b]) <= TOL_ERLE
+    # no echo output requested: same error signal, bit for bit; run-to-run determinism
+    e2 = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg, n_samples=None if ns is None else _cuda(ns))
+    assert np.array_equal(e2.cpu().numpy(), err)
+
+
+def test_overlap_save_pbfdaf_reaches_the_noise_floor_where_the_stft_recurrence_does_not():
+    """the reason algo 2 exists: single talk, 4 partitions, -40 dB noise"""
+    d = synth.make_batch(0, 4, 160000, rir_len=1024)
+    far, mic = _cuda(d["far"]), _cuda(d["mic"])
+    _, erle_ols = A.stage1_aec(far, mic, A.Stage1Config(algo=A.ALGO_PBFDAF, erle_skip_hops=250), return_erle=True)
+    _, erle_stft = A.stage1_aec(far, mic, A.Stage1Config(algo=A.ALGO_NLMS, erle_skip_hops=250), return_erle=True)
+    assert float(erle_ols.min()) > 35.0 and float(erle_stft.max()) < 20.0
+
+
 def test_batch_shift_matches_torch_and_stays_on_the_device():
     """ERB.py:254-256: mean / std (unbiased) over the whole batch tensor, reduced on the device (no host sync)"""
     g = torch.Generator(device="cuda").manual_seed(3)

@@ -82,3 +82,31 @@ def test_flop_model_matches_survey_table():
     assert O.flops_per_frame(O.AecConfig(partitions=4, algo=0)) == pytest.approx(56652)
     assert O.flops_per_frame(O.AecConfig(partitions=16, algo=1)) == pytest.approx(167419)
     assert O.flops_per_frame(O.AecConfig(frame=1024, partitions=8, algo=0)) == pytest.approx(153740)
+
+
+def test_overlap_save_pbfdaf_oracle_properties():
+    """algo = 2 (oracle only; the GPU parity tests compare the kernel with it): linear in the microphone, identity for a
+    silent far end, float32 tracks float64, and it reaches the -40 dB noise floor where the STFT-domain NLMS stays near
+    13 dB (the reason it exists)"""
+    from acoustic_echo_cancellation_b200 import synth
+
+    d = synth.make_utterance(3, 48000, rir_len=1024)
+    cfg = O.AecConfig(partitions=4, algo=O.ALGO_PBFDAF)
+    far, mic = d["far"].astype(np.float64), d["mic"].astype(np.float64)
+    e, yh = O.pbfdaf_ols(far, mic, cfg)
+    assert e.shape == yh.shape == (48000 // 256 * 256,)
+    assert np.abs(e + yh - mic[:e.size]).max() < 1e-12                       # e = d - y by construction
+    e0, y0 = O.pbfdaf_ols(np.zeros_like(far), mic, cfg)
+    assert np.array_equal(e0, mic[:e0.size]) and not y0.any()                # silent far end: identity
+    rng = np.random.default_rng(0)
+    mic2 = 0.05 * rng.standard_normal(mic.size)
+    ea, _ = O.pbfdaf_ols(far, mic2, cfg)
+    ec, _ = O.pbfdaf_ols(far, 0.5 * mic - 2.0 * mic2, cfg)
+    assert np.abs(ec - (0.5 * e - 2.0 * ea)).max() < 1e-10                   # the step does not depend on the microphone
+    e32, _ = O.pbfdaf_ols(far, mic, cfg, dtype=np.float32)
+    assert np.abs(e32 - e).max() < 1e-5
+    lo = 24000
+    erle = 10 * np.log10((mic[lo:e.size] ** 2).sum() / (e[lo:] ** 2).sum())
+    r = O.stage1(d["far"][None], d["mic"][None], O.AecConfig(partitions=4, algo=O.ALGO_NLMS))
+    erle_stft = 10 * np.log10((mic[lo:e.size] ** 2).sum() / (r["err"][0][lo:e.size] ** 2).sum())
+    assert erle > 33.0 and erle_stft < 20.0
