@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("AEC_B200_LIB") or os.path.join(_HERE, "libaec_b200.so
 ALGO_NLMS = 0
 ALGO_KALMAN = 1
 ALGO_PBFDAF = 2
+ALGO_PBFKF = 3
 
 
 class AecCfg(C.Structure):

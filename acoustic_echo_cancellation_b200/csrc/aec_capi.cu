@@ -277,7 +277,8 @@ static int validate_cfg(const aec_cfg* cfg) {
     if (!cfg) return AEC_EINVAL;
     if (cfg->frame != 512 && cfg->frame != 1024) return AEC_EUNSUPPORTED;
     if (cfg->partitions < 1) return AEC_EINVAL;
-    if (cfg->algo != AEC_ALGO_NLMS && cfg->algo != AEC_ALGO_KALMAN && cfg->algo != AEC_ALGO_PBFDAF) return AEC_EINVAL;
+    if (cfg->algo != AEC_ALGO_NLMS && cfg->algo != AEC_ALGO_KALMAN && cfg->algo != AEC_ALGO_PBFDAF && cfg->algo != AEC_ALGO_PBFKF)
+        return AEC_EINVAL;
     if (cfg->erle_skip_hops < 0) return AEC_EINVAL;
     return AEC_OK;
 }
@@ -368,9 +369,9 @@ static int stage1_run_impl(const float* far, const float* mic, float* err, float
         //  128 registers for the two-warp kernels so that 7 utterances stay resident per SM)
     }
     cudaError_t e;
-    if (cfg->algo == AEC_ALGO_PBFDAF) {
-        if (feat || wide) return AEC_EUNSUPPORTED;       // frame 512, no fused features for the overlap-save filter
-        e = launch_stage1_ols(P, echo, p, s);
+    if (cfg->algo == AEC_ALGO_PBFDAF || cfg->algo == AEC_ALGO_PBFKF) {
+        if (feat || wide) return AEC_EUNSUPPORTED;       // frame 512, no fused features for the overlap-save filters
+        e = launch_stage1_ols(P, cfg->algo == AEC_ALGO_PBFKF, echo, p, s);
     } else if (feat) {
         e = launch_stage1_feat(P, cfg->algo, p, s);
     } else if (wide) {

@@ -35,7 +35,7 @@
 
 namespace aec {
 
-enum { kAlgoNlms = 0, kAlgoKalman = 1, kAlgoPbfdaf = 2 };
+enum { kAlgoNlms = 0, kAlgoKalman = 1, kAlgoPbfdaf = 2, kAlgoPbfkf = 3 };
 
 // "this (P, algo, echo, register cap) is not instantiated": a code no launch path of the runtime produces
 constexpr cudaError_t kNoInstance = cudaErrorStubLibrary;

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ALGO_KALMAN, ALGO_NLMS, ALGO_PBFDAF  # noqa: F401  (re-exported)
+from ._lib import ALGO_KALMAN, ALGO_NLMS, ALGO_PBFDAF, ALGO_PBFKF  # noqa: F401  (re-exported)
 
 
 @dataclass

@@ -47,7 +47,7 @@ enum {
  * 2: overlap-save partitioned-block FDAF with the alternated gradient constraint -- time-domain blocks of hop new
  *    samples, FFT length frame, exact linear convolution (no analysis window; ~26 dB more ERLE on the single-talk set,
  *    DESIGN.md section 2); NLMS step on a smoothed input power.  Frame 512, partitions 1 / 2 / 4. */
-enum { AEC_ALGO_NLMS = 0, AEC_ALGO_KALMAN = 1, AEC_ALGO_PBFDAF = 2 };
+enum { AEC_ALGO_NLMS = 0, AEC_ALGO_KALMAN = 1, AEC_ALGO_PBFDAF = 2, AEC_ALGO_PBFKF = 3 };
 
 /* Parameter block of the stage-1 filter.  frame / hop follow the reference's
  * speech_conf (Stage2_lhm/scripts/configs.py:1-8: win_size 512, hop_size 256) and the window is

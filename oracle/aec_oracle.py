@@ -43,7 +43,8 @@ HOP_SIZE = 256
 
 ALGO_NLMS = 0
 ALGO_KALMAN = 1
-ALGO_PBFDAF = 2       # overlap-save constrained PBFDAF (round 2; time-domain blocks, no STFT framing)
+ALGO_PBFDAF = 2       # overlap-save constrained PBFDAF, NLMS step (round 2; time-domain blocks, no STFT framing)
+ALGO_PBFKF = 3        # the same filter with the diagonal Kalman step of algo 1
 
 
 @dataclass(frozen=True)
@@ -254,29 +255,47 @@ def fdaf_kalman(X: np.ndarray, Y: np.ndarray, cfg: AecConfig, dtype=np.float64):
 
 
 def pbfdaf_ols(far: np.ndarray, mic: np.ndarray, cfg: AecConfig, dtype=np.float64):
-    """Overlap-save partitioned-block FDAF with the alternated gradient constraint (algo = 2; BUILDER-AUTHORED,
-    parity unpinned like the other recurrences).  One utterance, time-domain in, time-domain out: blocks of
-    H = frame / 2 new samples, FFT length 2H = frame, P partitions -> the same P*H-sample tail as algos 0 / 1, but as
-    an exact linear convolution (no analysis window, no cross-band leakage).
+    """Overlap-save partitioned-block FDAF with the alternated gradient constraint (algo = 2: NLMS step, algo = 3:
+    the diagonal Kalman step of ``fdaf_kalman``; BUILDER-AUTHORED, parity unpinned like the other recurrences).  One
+    utterance, time-domain in, time-domain out: blocks of H = frame / 2 new samples, FFT length 2H = frame,
+    P partitions -> the same P*H-sample tail as algos 0 / 1, but as an exact linear convolution (no analysis window,
+    no cross-band leakage).
 
-    per block t (W_p = 0, Xh_p = 0, Pw = 0, x_{-1} = 0 initially):
+    per block t, c = t mod P (W_p = 0, Xh_p = 0, Pw = 0 / C_p = c0, Psi = 0, x_{-1} = 0 initially):
         Xh_p   = Xh_{p-1} (shift);  Xh_0 = rfft([x_{t-1}, x_t])
         y      = irfft(sum_p W_p Xh_p)[H:]           e = d_t - y            E = rfft([0_H, e])
+        W_c    = rfft(g),  g = irfft(W_c),  g[H:] = 0      (one partition constrained per block, AS IT ENTERED the
+                                                            block: the constraint does not wait for E, so a kernel
+                                                            runs its two transforms beside the two of the error path)
+      algo 2:
         Pw     = lam Pw + (1 - lam) sum_p |Xh_p|^2
         W_p   += mu / (Pw + delta) * conj(Xh_p) * E
-        c = t mod P:   g = irfft(W_c);  g[H:] = 0;  W_c = rfft(g)          (one partition constrained per block)
+      algo 3:
+        Psi    = lambda Psi + (1 - lambda) |E|^2
+        D      = sum_p C_p |Xh_p|^2 + Psi + eps          G_p = C_p conj(Xh_p) / D
+        W_p    = A (W_p + G_p E)
+        C_p    = A^2 (1 - C_p |Xh_p|^2 / D) C_p + (1 - A^2) |W_p|^2        (new W_p)
     Returns (err, yhat), each (n // H) * H samples."""
     cd = _cdtype(dtype)
     far = np.asarray(far, dtype=dtype)
     mic = np.asarray(mic, dtype=dtype)
     N, H, P = cfg.frame, cfg.hop, cfg.partitions
     K = H + 1
+    kalman = cfg.algo == ALGO_PBFKF
     nblk = min(len(far), len(mic)) // H
     W = np.zeros((P, K), dtype=cd)
     Xh = np.zeros((P, K), dtype=cd)
     pw = np.zeros(K, dtype=dtype)
+    C = np.full((P, K), cfg.kalman_c0, dtype=dtype)
+    psi = np.zeros(K, dtype=dtype)
     prev = np.zeros(H, dtype=dtype)
     mu, delta, lam = dtype(cfg.mu), dtype(cfg.delta), dtype(cfg.pb_lambda)
+    A = dtype(cfg.kalman_a)
+    A2 = dtype(cfg.kalman_a * cfg.kalman_a)
+    Q = dtype(1.0 - cfg.kalman_a * cfg.kalman_a)
+    klam = dtype(cfg.kalman_lambda)
+    koml = dtype(1.0 - cfg.kalman_lambda)
+    eps = dtype(cfg.kalman_eps)
     one = dtype(1.0)
     err = np.zeros(nblk * H, dtype=dtype)
     yh = np.zeros(nblk * H, dtype=dtype)
@@ -291,13 +310,23 @@ def pbfdaf_ols(far: np.ndarray, mic: np.ndarray, cfg: AecConfig, dtype=np.float6
         err[t * H:(t + 1) * H] = e
         yh[t * H:(t + 1) * H] = y
         E = np.fft.rfft(np.concatenate([zeros, e])).astype(cd)
-        pw = lam * pw + (one - lam) * (Xh.real ** 2 + Xh.imag ** 2).sum(axis=0).astype(dtype)
-        g = (mu / (pw + delta)).astype(dtype)
-        W = W + np.conj(Xh) * (g * E)[None, :]
         c = t % P
         gt = np.fft.irfft(W[c], n=N).astype(dtype)
         gt[H:] = 0
         W[c] = np.fft.rfft(gt).astype(cd)
+        x2 = (Xh.real ** 2 + Xh.imag ** 2).astype(dtype)
+        if not kalman:
+            pw = lam * pw + (one - lam) * x2.sum(axis=0)
+            g = (mu / (pw + delta)).astype(dtype)
+            W = W + np.conj(Xh) * (g * E)[None, :]
+        else:
+            psi = klam * psi + koml * (E.real ** 2 + E.imag ** 2).astype(dtype)
+            cx2 = C * x2
+            rD = one / (cx2.sum(axis=0) + psi + eps)
+            G = (C * rD[None, :]) * np.conj(Xh)
+            W = A * (W + G * E[None, :])
+            w2 = (W.real ** 2 + W.imag ** 2).astype(dtype)
+            C = A2 * (one - cx2 * rD[None, :]) * C + Q * w2
     return err, yh
 
 
@@ -336,7 +365,7 @@ def stage1(far: np.ndarray, mic: np.ndarray, cfg: AecConfig = AecConfig(),
     run = fdaf_nlms if cfg.algo == ALGO_NLMS else fdaf_kalman
     for b in range(B):
         n = int(n_samples[b])
-        if cfg.algo == ALGO_PBFDAF:             # time-domain blocks: (n // H) * H output samples, like (T - 1) * H
+        if cfg.algo in (ALGO_PBFDAF, ALGO_PBFKF):   # time-domain blocks: (n // H) * H output samples, like (T - 1) * H
             e, yh = pbfdaf_ols(far[b, :n], mic[b, :n], cfg, dtype)
             err[b, :e.shape[0]] = e
             echo[b, :yh.shape[0]] = yh

@@ -420,15 +420,16 @@ def test_fused_feature_epilogue_ragged_rows_and_golden_front_end(golden):
     assert float((f - want).abs().max()) <= 2e-5 * max(float(want.abs().max()), 1.0)
 
 
+@pytest.mark.parametrize("algo", [2, 3])
 @pytest.mark.parametrize("P,L,B", [(4, 16000 + 123, 3), (2, 8 * 256, 2), (1, 4097, 2), (4, 300, 2), (4, 160000, 2)])
-def test_overlap_save_pbfdaf_matches_oracle(P, L, B):
-    """algo = 2 (overlap-save PBFDAF, alternated constraint; builder-authored, parity unpinned): error signal, echo
-    estimate and ERLE against the float64 numpy oracle; same tolerance as the STFT-domain recurrences"""
+def test_overlap_save_pbfdaf_matches_oracle(P, L, B, algo):
+    """algo = 2 / 3 (overlap-save PBFDAF, alternated constraint, NLMS / Kalman step; builder-authored, parity unpinned):
+    error signal, echo estimate and ERLE against the float64 numpy oracle; same tolerance as the STFT-domain recurrences"""
     d = synth.make_batch(70, B, L, rir_len=min(P * 256, 1024))
     ns = np.array(([L, max(L - 777, 1), 255] * B)[:B], dtype=np.int64) if L < 100000 else None
     skip = 8
-    ref = O.stage1(d["far"], d["mic"], O.AecConfig(partitions=P, algo=O.ALGO_PBFDAF), n_samples=ns, erle_skip=skip * 256)
-    cfg = A.Stage1Config(partitions=P, algo=A.ALGO_PBFDAF, erle_skip_hops=skip)
+    ref = O.stage1(d["far"], d["mic"], O.AecConfig(partitions=P, algo=algo), n_samples=ns, erle_skip=skip * 256)
+    cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=skip)
     err, echo, erle = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg, n_samples=None if ns is None else _cuda(ns),
                                    return_echo=True, return_erle=True)
     torch.cuda.synchronize()
@@ -449,13 +450,50 @@ def test_overlap_save_pbfdaf_matches_oracle(P, L, B):
     assert np.array_equal(e2.cpu().numpy(), err)
 
 
+@pytest.mark.parametrize("algo", [2, 3])
+def test_overlap_save_unaligned_rows_and_batch_invariance(algo):
+    """rows that are not 16-byte aligned take the synchronous staging path; an utterance's result does not depend on
+    what else is in the batch"""
+    L = 20 * 256 + 77
+    d = synth.make_batch(90, 5, L, rir_len=1024)
+    cfg = A.Stage1Config(partitions=4, algo=algo)
+    far, mic = _cuda(d["far"]), _cuda(d["mic"])
+    base = A.stage1_aec(far, mic, cfg)
+    pad_f = torch.zeros(5, L + 3, device="cuda")
+    pad_m = torch.zeros(5, L + 3, device="cuda")
+    pad_f[:, 1:L + 1] = far
+    pad_m[:, 1:L + 1] = mic
+    odd = A.stage1_aec(pad_f[:, 1:L + 1], pad_m[:, 1:L + 1], cfg)
+    assert torch.equal(odd, base)
+    one = A.stage1_aec(far[3:4].contiguous(), mic[3:4].contiguous(), cfg)
+    assert torch.equal(one[0], base[3])
+
+
 def test_overlap_save_pbfdaf_reaches_the_noise_floor_where_the_stft_recurrence_does_not():
-    """the reason algo 2 exists: single talk, 4 partitions, -40 dB noise"""
+    """the reason algos 2 / 3 exist: single talk, 4 partitions, -40 dB noise"""
     d = synth.make_batch(0, 4, 160000, rir_len=1024)
     far, mic = _cuda(d["far"]), _cuda(d["mic"])
     _, erle_ols = A.stage1_aec(far, mic, A.Stage1Config(algo=A.ALGO_PBFDAF, erle_skip_hops=250), return_erle=True)
+    _, erle_kf = A.stage1_aec(far, mic, A.Stage1Config(algo=A.ALGO_PBFKF, erle_skip_hops=250), return_erle=True)
     _, erle_stft = A.stage1_aec(far, mic, A.Stage1Config(algo=A.ALGO_NLMS, erle_skip_hops=250), return_erle=True)
-    assert float(erle_ols.min()) > 35.0 and float(erle_stft.max()) < 20.0
+    assert float(erle_ols.min()) > 35.0 and float(erle_kf.min()) > 30.0 and float(erle_stft.max()) < 20.0
+
+
+def test_overlap_save_kalman_step_holds_through_double_talk():
+    """algo 3 vs algo 2 on the SURVEY 8d double-talk set: echo-only ERLE (echo vs echo - echo estimate) over the
+    double-talk span [0.4 L, 0.7 L]; the NLMS step is pulled away by the near end, the Kalman step is not"""
+    L = 160000
+    d = synth.make_batch(0, 4, L, rir_len=1024, double_talk=True)
+    far, mic = _cuda(d["far"]), _cuda(d["mic"])
+    a, b = int(0.4 * L), int(0.7 * L)
+
+    def dt_erle(algo):
+        _, echo = A.stage1_aec(far, mic, A.Stage1Config(algo=algo), return_echo=True)
+        res = d["echo"][:, a:b] - echo.cpu().numpy()[:, a:b]
+        return 10 * np.log10((d["echo"][:, a:b] ** 2).sum(1) / (res ** 2).sum(1))
+
+    nlms, kal = dt_erle(A.ALGO_PBFDAF), dt_erle(A.ALGO_PBFKF)
+    assert kal.min() > 10.0 and nlms.max() < 8.0 and (kal - nlms).min() > 5.0
 
 
 def test_batch_shift_matches_torch_and_stays_on_the_device():

@@ -1,0 +1,31 @@
+"""Device-timed throughput of the overlap-save kernels (algo 2 / 3) next to the STFT-domain NLMS kernel.
+    python tools/ols_time.py [B ...]
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import acoustic_echo_cancellation_b200 as A  # noqa: E402
+
+for B in [int(a) for a in sys.argv[1:]] or [1024, 4144]:
+    L = 160000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    far = 0.1 * torch.randn(B, L, device="cuda", generator=g)
+    mic = 0.5 * torch.roll(far, 37, dims=1) + 0.001 * torch.randn(B, L, device="cuda", generator=g)
+    out = torch.empty_like(far)
+    for algo, P in ((0, 4), (2, 4), (3, 4), (2, 2), (3, 2), (2, 1)):
+        cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=125)
+        for _ in range(3):
+            A.stage1_aec(far, mic, cfg, out=out, return_erle=True)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            e, erle = A.stage1_aec(far, mic, cfg, out=out, return_erle=True)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        print(f"B={B} algo={algo} P={P}: {ms:.3f} ms  {B * 10 / ms / 1e3:.2f} M audio-s/s  erle {float(erle.mean()):.1f} dB", flush=True)
+    del far, mic, out
