@@ -371,7 +371,7 @@ static int stage1_run_impl(const float* far, const float* mic, float* err, float
     cudaError_t e;
     if (cfg->algo == AEC_ALGO_PBFDAF || cfg->algo == AEC_ALGO_PBFKF) {
         if (feat || wide) return AEC_EUNSUPPORTED;       // frame 512, no fused features for the overlap-save filters
-        e = launch_stage1_ols(P, cfg->algo == AEC_ALGO_PBFKF, echo, p, s);
+        e = launch_stage1_ols(P, cfg->algo == AEC_ALGO_PBFKF, echo, cfg->variant > 0 ? cfg->variant % 1000 : 0, p, s);
     } else if (feat) {
         e = launch_stage1_feat(P, cfg->algo, p, s);
     } else if (wide) {

@@ -18,8 +18,19 @@ static cudaError_t launch_ols_p(bool kalman, bool echo, const Stage1Params& prm,
     return echo ? launch_ols<P, false, true, REGS_NLMS>(prm, s) : launch_ols<P, false, false, REGS_NLMS>(prm, s);
 }
 
-cudaError_t launch_stage1_ols(int P, bool kalman, bool echo, const Stage1Params& prm, cudaStream_t s) {
-    if (P == 4) return launch_ols_p<4, 128, 168>(kalman, echo, prm, s);
+// regs: register cap asked for through aec_cfg.variant (0 = the default below)
+cudaError_t launch_stage1_ols(int P, bool kalman, bool echo, int regs, const Stage1Params& prm, cudaStream_t s) {
+    if (P == 4) {
+        // four-partition Kalman step: 20 more state registers per thread.  The 128-register build (8 utterances per SM)
+        // spills ~50 values per block into L1, the 168-register one (6 per SM) is spill-free: 3.42 against 4.74 ms per
+        // 1024 x 10 s (the 168 build needs a second wave there), 12.4 against 11.9 ms per 4144 x 10 s -> 168 from 24
+        // utterances per SM on, 128 below.
+        if (kalman && regs == 0) regs = prm.B >= 24LL * prm.num_sms ? 168 : 128;
+        if (kalman && regs == 168) return launch_ols_p<4, 128, 168>(kalman, echo, prm, s);
+        if (regs == 0 || regs == 128) return launch_ols_p<4, 128, 128>(kalman, echo, prm, s);
+        return kNoInstance;
+    }
+    if (regs != 0 && regs != 128) return kNoInstance;
     if (P == 2) return launch_ols_p<2, 128, 128>(kalman, echo, prm, s);
     if (P == 1) return launch_ols_p<1, 128, 128>(kalman, echo, prm, s);
     return kNoInstance;

@@ -10,15 +10,20 @@
 //   * the constraint is applied to partition c = t mod P AS IT ENTERED the block (oracle/aec_oracle.py:pbfdaf_ols):
 //     it does not wait for E, so IFFT(W_c) runs on the upper half-warp beside IFFT(Yhat) on the lower one, and
 //     FFT(g) beside FFT([0, e]) -- one warp, two transform slots, both half-warps busy;
-//   * X_{t+1} = FFT[x_t, x_{t+1}] does not depend on the filter at all: the OTHER warp computes it during the same phase.
+//   * X_{t+1} = FFT[x_t, x_{t+1}] does not depend on the filter at all: the OTHER warp computes it during the same phase,
+//     two blocks at a time (X_{t+1} on its lower half-warp, X_{t+2} on the upper one, every second block).
 // Per block t, two block barriers:
 //   R  (64 threads, 4 bins each + bin 128): [t >= 1: E_{t-1}, constrained W_c back into registers, power / covariance,
 //      weight update]  then  X_t into the history, Yhat = sum_p W_p X_{t-p} packed for the inverse transform, W_c packed
 //   F  warp a = (slot + t) & 1:  y = IFFT(Yhat)[H:], e = d - y -> HBM, E = FFT[0, e]  ||  g = IFFT(W_c), g[H:] = 0, FFT(g)
-//      warp a ^ 1:               X_{t+1}
+//      warp a ^ 1, odd t:        X_{t+1} || X_{t+2}            (the forward transform is one shared body for both roles)
 // (a thread touches only its own bins' tile entries in R, so the update of block t-1 and the estimate of block t need
 // no barrier between them).  Far-end / microphone blocks are staged HBM -> shared memory with cp.async (LDGSTS, 16 B
-// per thread, no registers) two / one blocks ahead.
+// per thread, no registers) three / one blocks ahead.
+// Register layout of the taps: position j holds partition (j + t) mod P -- the weight update writes its result one
+// position down (a different destination register costs nothing), so the partition to constrain is always position 0;
+// the far-end history is a ring indexed by block mod P, which position j meets at slot (-j) mod P in every block.  Neither
+// the history nor the taps are ever shifted or selected by a run-time index; only the insertion of X_t is (P selects).
 // Why it exists: the STFT-domain recurrence (Hann analysis window, no cross-band terms) cancels ~13 dB on the SURVEY 8d
 // single-talk set; the exact linear convolution of this one reaches the 40 dB noise floor, and with the Kalman step it
 // holds 14 dB through double talk.
@@ -29,7 +34,7 @@
 namespace aec {
 
 struct OlsSmem {
-    static constexpr size_t tile_bytes = size_t(4) * kTilePitch * sizeof(float2);   // X, Yhat / E, W_c, scratch
+    static constexpr size_t tile_bytes = size_t(4) * kTilePitch * sizeof(float2);   // X [2], Yhat / E, W_c
     static constexpr size_t blk_bytes = size_t(4 + 2) * 256 * sizeof(float);        // far-end ring [4][256], microphone [2][256]
     __host__ __device__ static constexpr size_t total(int P) {
         return tile_bytes + blk_bytes + (size_t(P) * 20 + 16 + 15) / 16 * 16 + 64;
@@ -45,10 +50,15 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// weight update of one bin with the error spectrum E of the block (operation order of oracle/aec_oracle.py)
-template <int P, bool KAL>
+// Weight update of one bin with the error spectrum E of the block (operation order of oracle/aec_oracle.py).
+// ROT: W / C are in rotating positions (position j = partition (j + t) mod P), X is the ring (slot = block mod P):
+// position j meets slot (-j) mod P and the result goes one position down.  !ROT: W, C by partition, X by delay (bin 128).
+template <int P, bool KAL, bool ROT>
 __device__ __forceinline__ void ols_update(float2 (&W)[P], const float2 (&X)[P], float (&C)[KAL ? P : 1], float& sp,
                                            const float2 E, const Stage1Params& prm) {
+    auto xs = [&](int j) -> const float2& { return X[ROT ? (P - j) % P : j]; };
+    auto dst = [](int j) constexpr { return ROT ? (j + P - 1) % P : j; };
+    float2 Wn[P];
     if constexpr (!KAL) {
         float s = 0.f;
 #pragma unroll
@@ -57,40 +67,46 @@ __device__ __forceinline__ void ols_update(float2 (&W)[P], const float2 (&X)[P],
         const float g = prm.mu * rcp_fast(sp + prm.delta);
         const float2 ge = make_float2(g * E.x, g * E.y);
 #pragma unroll
-        for (int p = 0; p < P; ++p) W[p] = cfmac(X[p], ge, W[p]);
+        for (int j = 0; j < P; ++j) Wn[dst(j)] = cfmac(xs(j), ge, W[j]);
     } else {
+        float Cn[P];
         const float e2 = fmaf(E.x, E.x, E.y * E.y);
         sp = fmaf(prm.klam, sp, prm.koml * e2);
         float d = 0.f;
 #pragma unroll
-        for (int p = 0; p < P; ++p) d = fmaf(C[p], fmaf(X[p].x, X[p].x, X[p].y * X[p].y), d);
+        for (int j = 0; j < P; ++j) d = fmaf(C[j], fmaf(xs(j).x, xs(j).x, xs(j).y * xs(j).y), d);
         d = d + sp + prm.keps;
         const float rd = __frcp_rn(d);
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const float x2 = fmaf(X[p].x, X[p].x, X[p].y * X[p].y);
-            const float gs = C[p] * rd;
-            const float2 g = make_float2(gs * X[p].x, -gs * X[p].y);      // C conj(X) / D
-            float2 w = cfma(g, E, W[p]);
+        for (int j = 0; j < P; ++j) {
+            const float2 x = xs(j);
+            const float x2 = fmaf(x.x, x.x, x.y * x.y);
+            const float gs = C[j] * rd;
+            const float2 g = make_float2(gs * x.x, -gs * x.y);            // C conj(X) / D
+            float2 w = cfma(g, E, W[j]);
             w = make_float2(prm.ka * w.x, prm.ka * w.y);
-            W[p] = w;
-            C[p] = fmaf(prm.ka2 * (1.f - gs * x2), C[p], prm.kq * fmaf(w.x, w.x, w.y * w.y));
+            Wn[dst(j)] = w;
+            Cn[dst(j)] = fmaf(prm.ka2 * (1.f - gs * x2), C[j], prm.kq * fmaf(w.x, w.x, w.y * w.y));
         }
+#pragma unroll
+        for (int j = 0; j < P; ++j) C[j] = Cn[j];
     }
+#pragma unroll
+    for (int j = 0; j < P; ++j) W[j] = Wn[j];
 }
 
 template <int P, bool KAL, bool ECHO, int REGS>
 __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const Stage1Params prm) {
+    static_assert(P == 1 || P == 2 || P == 4, "partitions: a power of two, in registers");
     constexpr int PC = KAL ? P : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* tileX = reinterpret_cast<float2*>(smem_raw);
-    float2* tileY = tileX + kTilePitch;
+    float2* tileX = reinterpret_cast<float2*>(smem_raw);             // [2] spectra of the far-end blocks, slot = block & 1
+    float2* tileY = tileX + 2 * kTilePitch;
     float2* tileW = tileY + kTilePitch;
-    float2* tileS = tileW + kTilePitch;                              // exchange tile of the idle half-warp of the X transform
-    float* xring = reinterpret_cast<float*>(tileS + kTilePitch);     // [4][256] far-end blocks, slot = block & 3
+    float* xring = reinterpret_cast<float*>(tileW + kTilePitch);     // [4][256] far-end blocks, slot = block & 3
     float* dring = xring + 4 * 256;                                  // [2][256] microphone blocks, slot = block & 1
-    float2* midW = reinterpret_cast<float2*>(dring + 2 * 256);       // [P] taps of bin 128 (its own mirror)
-    float2* midX = midW + P;                                         // [P] its far-end history
+    float2* midW = reinterpret_cast<float2*>(dring + 2 * 256);       // [P] taps of bin 128 (its own mirror), by partition
+    float2* midX = midW + P;                                         // [P] its far-end history, slot = block mod P
     float* midC = reinterpret_cast<float*>(midX + P);                // [P] covariances (Kalman)
     float* midS = midC + P;                                          // [1] smoothed power / Psi
     float* red = midS + 1;                                           // [4] ERLE energies of the two warps
@@ -148,7 +164,6 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) wk[i] = __ldg(&prm.tw512[tid + 64 * i]);
-    const float2 w_mid = make_float2(0.f, -1.f);
 
     // block staging: 64 threads x 4 samples per signal
     auto stage_block = [&](const float* row, float* dst, int blk) {
@@ -162,116 +177,103 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
         }
     };
     stage_block(far_b, xring, 0);
+    stage_block(far_b, xring + 256, 1);
     cp_async_commit();
 
     float acc_m = 0.f, acc_e = 0.f;                                   // ERLE energies (lower half-warps)
     const float k512 = 1.0f / 512.0f;
 
     for (int t = -1; t < nblk; ++t) {
-        stage_block(far_b, xring + ((t + 2) & 3) * 256, t + 2);
+        stage_block(far_b, xring + ((t + 3) & 3) * 256, t + 3);
         stage_block(mic_b, dring + ((t + 1) & 1) * 256, t + 1);
         cp_async_commit();
         const int a = (fw + t) & 1;                                   // the warp that carries the chain of this block
         // ---- R: update with E_{t-1}, echo estimate of block t ----
         if (t >= 0) {
-            const int c = t % P, cprev = (t + P - 1) % P;
+            const int c = t & (P - 1);                                // partition constrained in this block = ring slot of X_t
+            const float2* tX = tileX + (t & 1) * kTilePitch;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int k = tid + 64 * i, km = (256 - k) & 255;
                 if (t >= 1) {
-                    float2 ek, em, ca, cb;
+                    float2 ek, em;
                     unpack_pair(tileY[k], tileY[km], wk[i], ek, em);
-                    unpack_pair(tileW[k], tileW[km], wk[i], ca, cb);
-#pragma unroll
-                    for (int p = 0; p < P; ++p)
-                        if (cprev == p) {
-                            W[2 * i][p] = ca;
-                            W[2 * i + 1][p] = cb;
-                        }
-                    ols_update<P, KAL>(W[2 * i], X[2 * i], C[2 * i], sp[2 * i], ek, prm);
-                    ols_update<P, KAL>(W[2 * i + 1], X[2 * i + 1], C[2 * i + 1], sp[2 * i + 1], em, prm);
+                    unpack_pair(tileW[k], tileW[km], wk[i], W[2 * i][0], W[2 * i + 1][0]);   // the constrained partition
+                    ols_update<P, KAL, true>(W[2 * i], X[2 * i], C[2 * i], sp[2 * i], ek, prm);
+                    ols_update<P, KAL, true>(W[2 * i + 1], X[2 * i + 1], C[2 * i + 1], sp[2 * i + 1], em, prm);
                 }
                 float2 xk, xm, gk, gm;
-                unpack_pair(tileX[k], tileX[km], wk[i], xk, xm);
+                unpack_pair(tX[k], tX[km], wk[i], xk, xm);
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    float2* Xb = X[2 * i + b];
-#pragma unroll
-                    for (int p = P - 1; p > 0; --p) Xb[p] = Xb[p - 1];
-                    Xb[0] = b ? xm : xk;
-                }
+                for (int s = 0; s < P; ++s)
+                    if (c == s) {
+                        X[2 * i][s] = xk;
+                        X[2 * i + 1][s] = xm;
+                    }
                 float2 yk = make_float2(0.f, 0.f), ym = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    yk = cfma(W[2 * i][p], X[2 * i][p], yk);
-                    ym = cfma(W[2 * i + 1][p], X[2 * i + 1][p], ym);
+                for (int j = 0; j < P; ++j) {
+                    yk = cfma(W[2 * i][j], X[2 * i][(P - j) % P], yk);
+                    ym = cfma(W[2 * i + 1][j], X[2 * i + 1][(P - j) % P], ym);
                 }
                 pack_pair(yk, ym, wk[i], gk, gm);
                 tileY[k] = gk;
                 tileY[km] = gm;
-                float2 wa = W[2 * i][0], wb = W[2 * i + 1][0];
-#pragma unroll
-                for (int p = 1; p < P; ++p)
-                    if (c == p) {
-                        wa = W[2 * i][p];
-                        wb = W[2 * i + 1][p];
-                    }
-                pack_pair(wa, wb, wk[i], gk, gm);
+                pack_pair(W[2 * i][0], W[2 * i + 1][0], wk[i], gk, gm);
                 tileW[k] = gk;
                 tileW[km] = gm;
             }
             if (tid == (a ^ 1) * 32 + 31) {                           // bin 128, on the warp with the lighter transform phase
-                float2 xk, xm, gk, gm;
-                float2 mw[P], mx[P];
+                // its split / packing twiddle is -i: the real-signal bin is 2 conj(Z[128]), and back (exact, no multiplies)
+                auto conj2 = [](float2 z) { return make_float2(2.f * z.x, -2.f * z.y); };
+                float2 mw[P], mx[P];                                  // by partition / by delay (as of block t - 1)
                 float mc[PC], ms = *midS;
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     mw[p] = midW[p];
-                    mx[p] = midX[p];
+                    mx[p] = midX[(t - 1 - p) & (P - 1)];
                 }
 #pragma unroll
                 for (int p = 0; p < PC; ++p) mc[p] = midC[p];
                 if (t >= 1) {
-                    float2 ek, em, ca, cb;
-                    unpack_pair(tileY[128], tileY[128], w_mid, ek, em);
-                    unpack_pair(tileW[128], tileW[128], w_mid, ca, cb);
+                    const float2 ek = conj2(tileY[128]), ca = conj2(tileW[128]);
+                    const int cprev = (t - 1) & (P - 1);
 #pragma unroll
                     for (int p = 0; p < P; ++p)
                         if (cprev == p) mw[p] = ca;
-                    ols_update<P, KAL>(mw, mx, mc, ms, ek, prm);
+                    ols_update<P, KAL, false>(mw, mx, mc, ms, ek, prm);
                     *midS = ms;
 #pragma unroll
                     for (int p = 0; p < PC; ++p) midC[p] = mc[p];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) midW[p] = mw[p];
                 }
-                unpack_pair(tileX[128], tileX[128], w_mid, xk, xm);
+                const float2 xk = conj2(tX[128]);
 #pragma unroll
                 for (int p = P - 1; p > 0; --p) mx[p] = mx[p - 1];
                 mx[0] = xk;
+                midX[c] = xk;
                 float2 y = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int p = 0; p < P; ++p) y = cfma(mw[p], mx[p], y);
-                pack_pair(y, y, w_mid, gk, gm);
-                tileY[128] = gk;
+                tileY[128] = conj2(y);
                 float2 wc = mw[0];
 #pragma unroll
                 for (int p = 1; p < P; ++p)
                     if (c == p) wc = mw[p];
-                pack_pair(wc, wc, w_mid, gk, gm);
-                tileW[128] = gk;
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    midW[p] = mw[p];
-                    midX[p] = mx[p];
-                }
+                tileW[128] = conj2(wc);
             }
         }
         cp_async_wait<1>();                                           // blocks staged one iteration ago have landed
         __syncthreads();
-        // ---- F: the two transform slots of the chain on warp a, X_{t+1} on the other warp ----
-        if (warp == a) {
-            if (t >= 0) {
-                float2 v[16];
-                float2* tile = half == 0 ? tileY : tileW;             // lower half-warp: error path; upper: constraint
+        // ---- F: the two transform slots of the chain on warp a; X_{t+1}, X_{t+2} on the other warp (odd t) ----
+        const bool chain = (warp == a) && (t >= 0);
+        const bool xjob = (warp != a) && (t & 1) && (t + 1 < nblk);
+        if (chain || xjob) {
+            float2 v[16];
+            float2* tile;
+            if (chain) {
+                tile = half == 0 ? tileY : tileW;                     // lower half-warp: error path; upper: constraint
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = tile[h + 16 * j];
                 __syncwarp();
@@ -308,24 +310,21 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
                     acc_m += em;
                     acc_e += ee;
                 }
-                __syncwarp();
-                fft256_halfwarp_regs<false>(v, tile, twr, h);
+            } else {
+                // X_b = FFT[x_{b-1}, x_b], b = t + 1 (lower half-warp), t + 2 (upper); the 0.5 of the real-FFT split rides
+                // on the input
+                const int b1 = t + 1 + half;
+                tile = tileX + (b1 & 1) * kTilePitch;
+                const float* prev = xring + ((b1 - 1) & 3) * 256 + 2 * h;
+                const float* cur = xring + (b1 & 3) * 256 + 2 * h;
 #pragma unroll
-                for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
+                for (int j = 0; j < 16; ++j) {
+                    const float2 x = *reinterpret_cast<const float2*>((j < 8 ? prev : cur) + 32 * (j & 7));
+                    v[j] = make_float2(0.5f * x.x, 0.5f * x.y);
+                }
             }
-        } else if (t + 1 < nblk) {
-            // X_{t+1} = FFT[x_t, x_{t+1}]  (the 0.5 of the real-FFT split rides on the input; the upper half-warp
-            // transforms along into the scratch tile)
-            float2 v[16];
-            const float* prev = xring + (t & 3) * 256 + 2 * h;
-            const float* cur = xring + ((t + 1) & 3) * 256 + 2 * h;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 x = *reinterpret_cast<const float2*>((j < 8 ? prev : cur) + 32 * (j & 7));
-                v[j] = make_float2(0.5f * x.x, 0.5f * x.y);
-            }
-            float2* tile = half == 0 ? tileX : tileS;
-            fft256_halfwarp_regs<false>(v, tile, twr, h);
+            __syncwarp();
+            fft256_halfwarp_regs<false>(v, tile, twr, h);             // one body for both roles
 #pragma unroll
             for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
         }
@@ -355,6 +354,6 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
 }
 
 // stage1_inst_ols.cu
-cudaError_t launch_stage1_ols(int P, bool kalman, bool echo, const Stage1Params& prm, cudaStream_t s);
+cudaError_t launch_stage1_ols(int P, bool kalman, bool echo, int regs, const Stage1Params& prm, cudaStream_t s);
 
 }  // namespace aec

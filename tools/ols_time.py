@@ -15,8 +15,8 @@ for B in [int(a) for a in sys.argv[1:]] or [1024, 4144]:
     far = 0.1 * torch.randn(B, L, device="cuda", generator=g)
     mic = 0.5 * torch.roll(far, 37, dims=1) + 0.001 * torch.randn(B, L, device="cuda", generator=g)
     out = torch.empty_like(far)
-    for algo, P in ((0, 4), (2, 4), (3, 4), (2, 2), (3, 2), (2, 1)):
-        cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=125)
+    for algo, P, var in ((0, 4, 0), (2, 4, 0), (3, 4, 0), (3, 4, 2128), (3, 4, 2168), (2, 2, 0), (3, 2, 0), (2, 1, 0)):
+        cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=125, variant=var)
         for _ in range(3):
             A.stage1_aec(far, mic, cfg, out=out, return_erle=True)
         torch.cuda.synchronize()
@@ -27,5 +27,5 @@ for B in [int(a) for a in sys.argv[1:]] or [1024, 4144]:
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 5
-        print(f"B={B} algo={algo} P={P}: {ms:.3f} ms  {B * 10 / ms / 1e3:.2f} M audio-s/s  erle {float(erle.mean()):.1f} dB", flush=True)
+        print(f"B={B} algo={algo} P={P} variant={var}: {ms:.3f} ms  {B * 10 / ms / 1e3:.2f} M audio-s/s  erle {float(erle.mean()):.1f} dB", flush=True)
     del far, mic, out

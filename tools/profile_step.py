@@ -15,10 +15,16 @@ ap.add_argument("--config", type=int, default=2)
 ap.add_argument("--launches", type=int, default=4)
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--batch", type=int, default=0)
+ap.add_argument("--algo", type=int, default=-1)
+ap.add_argument("--partitions", type=int, default=0)
 a = ap.parse_args()
 B, P, algo = (1024, 4, 0) if a.config == 2 else (4096, 16, 1)
 if a.batch:
     B = a.batch
+if a.algo >= 0:
+    algo = a.algo
+if a.partitions:
+    P = a.partitions
 L = 160000
 g = torch.Generator(device="cuda").manual_seed(1)
 far = 0.1 * torch.randn(B, L, device="cuda", generator=g)
