@@ -28,6 +28,9 @@ cudaError_t launch_stage1_ols(int P, bool kalman, bool echo, int regs, const Sta
         if (kalman && regs == 0) regs = prm.B >= 24LL * prm.num_sms ? 168 : 128;
         if (kalman && regs == 168) return launch_ols_p<4, 128, 168>(kalman, echo, prm, s);
         if (regs == 0 || regs == 128) return launch_ols_p<4, 128, 128>(kalman, echo, prm, s);
+        // (NLMS step at 168 registers, spill-free: 6 % shorter block latency -- 3660 against 3900 cycles alone on an SM --
+        //  which does not pay for 6 instead of 8 resident utterances; variant 2168)
+        if (!kalman && regs == 168) return launch_ols_p<4, 168, 168>(kalman, echo, prm, s);
         return kNoInstance;
     }
     if (regs != 0 && regs != 128) return kNoInstance;

@@ -138,6 +138,13 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
     }
     if (tid == 0) *midS = 0.f;
     for (int i = tid; i < 256; i += 64) xring[3 * 256 + i] = 0.f;    // x_{-1} = 0 (slot of block -1)
+#ifdef AEC_PHASE_TIMING
+    __shared__ long long dbg_sm[2][12];
+    if (lane == 0) {
+        for (int i = 0; i < 11; ++i) dbg_sm[warp][i] = 0;
+        dbg_sm[warp][11] = clock64();
+    }
+#endif
     __syncthreads();
     const int fw = *fft_warp_s;
 
@@ -264,8 +271,10 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
                 tileW[128] = conj2(wc);
             }
         }
+        AEC_TICK(0);                                                  // R
         cp_async_wait<1>();                                           // blocks staged one iteration ago have landed
         __syncthreads();
+        AEC_TICK(1);                                                  // wait after R
         // ---- F: the two transform slots of the chain on warp a; X_{t+1}, X_{t+2} on the other warp (odd t) ----
         const bool chain = (warp == a) && (t >= 0);
         const bool xjob = (warp != a) && (t & 1) && (t + 1 < nblk);
@@ -328,7 +337,13 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
 #pragma unroll
             for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
         }
+#ifdef AEC_PHASE_TIMING
+        if (warp == a) AEC_TICK(2); else AEC_TICK(4);                 // F as the chain warp / as the other warp
+#endif
         __syncthreads();
+#ifdef AEC_PHASE_TIMING
+        if (warp == a) AEC_TICK(3); else AEC_TICK(5);                 // wait after F
+#endif
     }
     cp_async_wait<0>();
 
@@ -351,6 +366,10 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
         if (tid == 0)
             prm.erle_db[blockIdx.x] = 10.f * log10f(fmaxf(red[0] + red[2], 1e-20f) / fmaxf(red[1] + red[3], 1e-20f));
     }
+#ifdef AEC_PHASE_TIMING
+    if (lane == 0 && prm.dbg)
+        for (int i = 0; i < 12; ++i) prm.dbg[((long long)blockIdx.x * 2 + warp) * 12 + i] = dbg_sm[warp][i];
+#endif
 }
 
 // stage1_inst_ols.cu

@@ -521,10 +521,26 @@ def build_parser(kind: str) -> argparse.ArgumentParser:
         p.add_argument("--h5_path", type=str, default="/data/lihaoming/datasets/synthetic/h5")
     p.add_argument("--list_path", type=str, default="../examples/filelists")
     p.add_argument("--sr", type=int, default=16000)
+    # not in the reference (which has no stage 1): which filter produces stage1_error / stage1_echo
+    p.add_argument("--stage1_algo", choices=sorted(STAGE1_ALGOS), default="nlms",
+                   help="nlms / kalman: STFT-domain recurrence; ols-nlms / ols-kalman: overlap-save PBFDAF (frame 512, <= 4 partitions)")
+    p.add_argument("--stage1_partitions", type=int, default=4)
     return p
+
+
+STAGE1_ALGOS = {"nlms": 0, "kalman": 1, "ols-nlms": 2, "ols-kalman": 3}
+
+
+def runner_from_args(args) -> Optional[Callable]:
+    """the stage-1 runner the command-line flags ask for; None (-> library default) when they are absent"""
+    if not hasattr(args, "stage1_algo"):
+        return None
+    from .stage1 import Stage1Config
+
+    return default_runner(Stage1Config(algo=STAGE1_ALGOS[args.stage1_algo], partitions=int(args.stage1_partitions)))
 
 
 def main(kind: str = "train", argv=None):
     args = build_parser(kind).parse_args(argv)
     os.makedirs(args.h5_path, exist_ok=True)
-    return {"train": create_h5_train, "test": create_h5_test, "val": create_h5_val}[kind](args)
+    return {"train": create_h5_train, "test": create_h5_test, "val": create_h5_val}[kind](args, runner=runner_from_args(args))

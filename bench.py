@@ -45,8 +45,11 @@ WORKLOADS = {
 def flops_per_frame(N, P, algo):
     import math
     K = N // 2 + 1
-    common = 7.5 * N * math.log2(N) + 5 * N
-    return common + (16 * K * P + 12 * K if algo == 0 else 31 * K * P + 11 * K)
+    if algo >= 2:       # overlap-save filter: five real transforms per block (X, y, E, the two of the constraint), no windows
+        common = 12.5 * N * math.log2(N) + 2 * N
+    else:
+        common = 7.5 * N * math.log2(N) + 5 * N
+    return common + (16 * K * P + 12 * K if algo in (0, 2) else 31 * K * P + 11 * K)
 
 
 class ClockSampler:
@@ -166,7 +169,7 @@ def workload_config(wl, world):
     """`config` of the JSON line -- identical for both arms."""
     B, L, SR, FRAME = wl["B"], wl["L"], wl["sr"], wl["frame"]
     return {"workload": wl["name"], "utterances_per_gpu": B, "samples": L, "sample_rate": SR,
-            "frame": FRAME, "hop": FRAME // 2, "partitions": wl["P"], "algo": "nlms" if wl["algo"] == 0 else "kalman",
+            "frame": FRAME, "hop": FRAME // 2, "partitions": wl["P"], "algo": ("nlms", "kalman", "ols-nlms", "ols-kalman")[wl["algo"]],
             "generator": "bench.make_inputs (SURVEY 8d recipe, CPU-seeded draws, seed 1000 + rank)",
             "l2": "inputs %.1f GB/GPU per step >> 126 MB L2 (no flush needed)" % (2 * B * L * 4 / 1e9),
             "parallelism": f"utterance-sharded x{world}, metrics-only all_gather"}
@@ -328,13 +331,14 @@ def device_timed(A, torch, dist, sharding, far, mic, err, cfg, steps, world, n_t
 
 
 def roofline_of(wl, kern_ms, fp32_peak, hbm_peak, hbm_src, traffic=None):
-    frames = wl["L"] // (wl["frame"] // 2) + 1
+    frames = wl["L"] // (wl["frame"] // 2) + (1 if wl["algo"] < 2 else 0)     # overlap-save: whole blocks only
     flops_launch = flops_per_frame(wl["frame"], wl["P"], wl["algo"]) * frames * wl["B"]
     bytes_launch = 3 * 4 * wl["L"] * wl["B"]
     tf = flops_launch / (kern_ms * 1e-3) / 1e12
     gbs = bytes_launch / (kern_ms * 1e-3) / 1e9
     return {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
-            "traffic": traffic, "kernel": "aec::stage1_n%d_kernel" % wl["frame"], "kernel_ms": kern_ms,
+            "traffic": traffic, "kernel": "aec::stage1_n%d_kernel" % wl["frame"] if wl["algo"] < 2 else "aec::stage1_ols_kernel",
+            "kernel_ms": kern_ms,
             "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
             "peak_source": "FFMA probe measured live in this run (aec_bench_fp32_peak; FFMAs with constant operands -- "
                            "FFMAs with three register sources issue at 0.64 of it, profiles/r2_ffma_reuse.txt); "
@@ -390,6 +394,10 @@ def also_rows(A, torch, sharding, args, fp32_peak, hbm_peak, hbm_src, local):
     rows = []
     extra = [dict(WORKLOADS[3]), dict(WORKLOADS[4]),
              dict(WORKLOADS[2], B=4144, name="many waves: 4144 x 10 s utterances (28 per SM), 16 kHz, 4-partition FDAF-NLMS"),
+             dict(WORKLOADS[2], algo=2, name="configs[1] through the overlap-save PBFDAF (algo 2: exact linear convolution, "
+                                             "alternated constraint, NLMS step; ~38 dB ERLE where the STFT-domain filter "
+                                             "reaches 13)"),
+             dict(WORKLOADS[2], algo=3, name="configs[1] through the overlap-save PBFDAF with the Kalman step (algo 3)"),
              dict(WORKLOADS[2], feat=True, name="configs[1] with the Stage-2 feature front end fused into the kernel "
                                                 "(aec_stage1_run_features: error signal + [B, T, 64] features per launch)")]
     for wl in extra:

@@ -489,8 +489,11 @@ def stage2_little_net(mic: np.ndarray, ref: np.ndarray, erb: np.ndarray, w: dict
 # --------------------------------------------------------------------------------------
 def flops_per_frame(cfg: AecConfig) -> float:
     n, k, p = cfg.frame, cfg.bins, cfg.partitions
-    common = 7.5 * n * math.log2(n) + 5 * n
-    if cfg.algo == ALGO_NLMS:
+    if cfg.algo in (ALGO_PBFDAF, ALGO_PBFKF):     # per block: five real transforms (X, y, E, two of the constraint), no windows
+        common = 12.5 * n * math.log2(n) + 2 * n
+    else:
+        common = 7.5 * n * math.log2(n) + 5 * n
+    if cfg.algo in (ALGO_NLMS, ALGO_PBFDAF):
         return common + 16 * k * p + 12 * k
     return common + 31 * k * p + 11 * k
 

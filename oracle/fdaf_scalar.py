@@ -113,3 +113,85 @@ def stage1_scalar(far: List[float], mic: List[float], partitions: int = 4, algo:
     pe = sum(v * v for v in err[lo:])
     erle = 10.0 * math.log10(max(pm, 1e-20) / max(pe, 1e-20))
     return err, echo, erle
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# algo = 2 / 3: overlap-save partitioned-block FDAF, alternated constraint applied to the partition as it entered the block
+# (DESIGN.md section 2b).  Same rules as above: plain Python, direct-sum transforms over a cosine / sine table, one bin and
+# one tap at a time, nothing shared with aec_oracle.py.
+# ----------------------------------------------------------------------------------------------------------------------
+def _rdft(x: List[float], cos_t, sin_t) -> List[complex]:
+    return [complex(sum(v * c for v, c in zip(x, cos_t[k])), -sum(v * s for v, s in zip(x, sin_t[k])))
+            for k in range(len(cos_t))]
+
+
+def _irdft(spec: List[complex], n: int, cos_t, sin_t) -> List[float]:
+    half = n // 2
+    out = []
+    for i in range(n):
+        s = spec[0].real + spec[half].real * (1.0 if i % 2 == 0 else -1.0)
+        for k in range(1, half):
+            s += 2.0 * (spec[k].real * cos_t[k][i] - spec[k].imag * sin_t[k][i])
+        out.append(s / n)
+    return out
+
+
+def stage1_ols_scalar(far: List[float], mic: List[float], partitions: int = 4, algo: int = 2, frame: int = 512,
+                      mu: float = 0.5, delta: float = None, pb_lambda: float = 0.5, a: float = 0.999, lam: float = 0.9,
+                      c0: float = 1.0, eps: float = 1e-10, erle_skip_hops: int = 0) -> Tuple[List[float], List[float], float]:
+    """(error signal, echo estimate, ERLE in dB) of ONE utterance.  ``algo`` 2 = NLMS step on a smoothed input power,
+    3 = diagonal Kalman step.  Blocks of frame / 2 new samples; outputs cover the whole blocks only."""
+    n, hop, bins = frame, frame // 2, frame // 2 + 1
+    delta = 1e-6 * n if delta is None else delta
+    _, cos_t, sin_t = _tables(n)
+    blocks = min(len(far), len(mic)) // hop
+    w = [[0j] * bins for _ in range(partitions)]            # taps, by partition
+    cov = [[c0] * bins for _ in range(partitions)]
+    power = [0.0] * bins                                    # smoothed input power (algo 2) / Psi (algo 3)
+    spectra = []                                            # far-end spectra of the blocks so far
+    err, echo = [], []
+    for t in range(blocks):
+        older = list(far[(t - 1) * hop:t * hop]) if t > 0 else [0.0] * hop
+        newer = list(far[t * hop:(t + 1) * hop])
+        spectra.append(_rdft(older + newer, cos_t, sin_t))
+        past = [spectra[t - p] if t - p >= 0 else [0j] * bins for p in range(partitions)]
+        yhat_spec = []
+        for k in range(bins):
+            acc = 0j
+            for p in range(partitions):
+                acc += w[p][k] * past[p][k]
+            yhat_spec.append(acc)
+        y = _irdft(yhat_spec, n, cos_t, sin_t)[hop:]
+        d = list(mic[t * hop:(t + 1) * hop])
+        e = [dv - yv for dv, yv in zip(d, y)]
+        err.extend(e)
+        echo.extend(y)
+        e_spec = _rdft([0.0] * hop + e, cos_t, sin_t)
+        # the partition whose turn it is loses the second half of its impulse response -- before this block's update
+        c = t % partitions
+        g = _irdft(w[c], n, cos_t, sin_t)
+        w[c] = _rdft(g[:hop] + [0.0] * hop, cos_t, sin_t)
+        for k in range(bins):
+            if algo == 2:
+                total = 0.0
+                for p in range(partitions):
+                    total += abs(past[p][k]) ** 2
+                power[k] = pb_lambda * power[k] + (1.0 - pb_lambda) * total
+                step = mu / (power[k] + delta)
+                for p in range(partitions):
+                    w[p][k] = w[p][k] + step * past[p][k].conjugate() * e_spec[k]
+            else:
+                power[k] = lam * power[k] + (1.0 - lam) * abs(e_spec[k]) ** 2
+                den = power[k] + eps
+                for p in range(partitions):
+                    den += cov[p][k] * abs(past[p][k]) ** 2
+                for p in range(partitions):
+                    x2 = abs(past[p][k]) ** 2
+                    gain = cov[p][k] * past[p][k].conjugate() / den
+                    w[p][k] = a * (w[p][k] + gain * e_spec[k])
+                    cov[p][k] = a * a * (1.0 - cov[p][k] * x2 / den) * cov[p][k] + (1.0 - a * a) * abs(w[p][k]) ** 2
+    lo = erle_skip_hops * hop
+    pm = sum(v * v for v in mic[lo:len(err)])
+    pe = sum(v * v for v in err[lo:])
+    erle = 10.0 * math.log10(max(pm, 1e-20) / max(pe, 1e-20))
+    return err, echo, erle

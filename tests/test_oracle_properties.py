@@ -82,6 +82,12 @@ def test_flop_model_matches_survey_table():
     assert O.flops_per_frame(O.AecConfig(partitions=4, algo=0)) == pytest.approx(56652)
     assert O.flops_per_frame(O.AecConfig(partitions=16, algo=1)) == pytest.approx(167419)
     assert O.flops_per_frame(O.AecConfig(frame=1024, partitions=8, algo=0)) == pytest.approx(153740)
+    # overlap-save filters (builder's count, same conventions): 12.5 N log2 N + 2 N + the recurrence terms
+    assert O.flops_per_frame(O.AecConfig(partitions=4, algo=O.ALGO_PBFDAF)) == pytest.approx(78156)
+    assert O.flops_per_frame(O.AecConfig(partitions=4, algo=O.ALGO_PBFKF)) == pytest.approx(93319)
+    import bench
+    for algo in (0, 1, 2, 3):
+        assert bench.flops_per_frame(512, 4, algo) == pytest.approx(O.flops_per_frame(O.AecConfig(partitions=4, algo=algo)))
 
 
 def test_overlap_save_pbfdaf_oracle_properties():
@@ -105,7 +111,16 @@ def test_overlap_save_pbfdaf_oracle_properties():
     assert np.abs(ec - (0.5 * e - 2.0 * ea)).max() < 1e-10                   # the step does not depend on the microphone
     e32, _ = O.pbfdaf_ols(far, mic, cfg, dtype=np.float32)
     assert np.abs(e32 - e).max() < 1e-5
+    # algo 3 (Kalman step): identity for a silent far end, float32 tracks float64, e + y = d
+    kcfg = O.AecConfig(partitions=4, algo=O.ALGO_PBFKF)
+    ek, yk = O.pbfdaf_ols(far, mic, kcfg)
+    assert np.abs(ek + yk - mic[:ek.size]).max() < 1e-12
+    ek0, yk0 = O.pbfdaf_ols(np.zeros_like(far), mic, kcfg)
+    assert np.array_equal(ek0, mic[:ek0.size]) and not yk0.any()
+    ek32, _ = O.pbfdaf_ols(far, mic, kcfg, dtype=np.float32)
+    assert np.abs(ek32 - ek).max() < 1e-5
     lo = 24000
+    assert 10 * np.log10((mic[lo:ek.size] ** 2).sum() / (ek[lo:] ** 2).sum()) > 20.0      # 25 dB after 1.5 s (35 after 4)
     erle = 10 * np.log10((mic[lo:e.size] ** 2).sum() / (e[lo:] ** 2).sum())
     r = O.stage1(d["far"][None], d["mic"][None], O.AecConfig(partitions=4, algo=O.ALGO_NLMS))
     erle_stft = 10 * np.log10((mic[lo:e.size] ** 2).sum() / (r["err"][0][lo:e.size] ** 2).sum())

@@ -1,7 +1,7 @@
 """Parity hardening for the (unpinned) FDAF recurrence: a second restatement of DESIGN.md section 2, written one bin
 and one tap at a time in plain Python with direct-sum transforms and no helper shared with the numpy oracle
 (oracle/fdaf_scalar.py), must agree with the numpy oracle (CPU) and with the CUDA path (GPU) -- 3 seeds x
-{NLMS, Kalman}.  A mistake the oracle and the kernels share because one hand wrote both would show up here."""
+{NLMS, Kalman} for the STFT-domain recurrence, 2 seeds x {NLMS, Kalman step} for the overlap-save filter.  A mistake the oracle and the kernels share because one hand wrote both would show up here."""
 import numpy as np
 import pytest
 
@@ -10,7 +10,7 @@ from oracle import aec_oracle as O
 from oracle import fdaf_scalar as S
 
 L = 2500          # not a multiple of the hop; 10 frames
-CASES = [(seed, algo) for seed in (0, 1, 2) for algo in (0, 1)]
+CASES = [(seed, algo) for seed in (0, 1, 2) for algo in (0, 1)] + [(seed, algo) for seed in (0, 2) for algo in (2, 3)]
 _cache = {}
 
 
@@ -19,7 +19,8 @@ def _scalar(seed, algo, P=4):
     if key not in _cache:
         d = synth.make_utterance(100 + seed, L, rir_len=512, double_talk=(seed == 2))
         far, mic = d["far"].astype(np.float64), d["mic"].astype(np.float64)
-        err, echo, erle = S.stage1_scalar(list(far), list(mic), partitions=P, algo=algo, erle_skip_hops=2)
+        run = S.stage1_scalar if algo < 2 else S.stage1_ols_scalar      # algos 2 / 3: overlap-save filter
+        err, echo, erle = run(list(far), list(mic), partitions=P, algo=algo, erle_skip_hops=2)
         _cache[key] = (d, np.array(err), np.array(echo), erle)
     return _cache[key]
 

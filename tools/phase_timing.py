@@ -36,7 +36,7 @@ def main():
     setter = lib.aec_debug_set_phase_buffer
     setter.argtypes = [C.c_void_p]
     setter.restype = None
-    nw = args.variant // 1000
+    nw = args.variant // 1000 if args.algo < 2 else 2
     L = args.samples
     frames = L // 256 + 1
     for B in [int(x) for x in args.batches.split(",")]:
@@ -56,6 +56,15 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         setter(None)
+        if args.algo >= 2:      # overlap-save kernels: two phases per block, the warps swap roles every block
+            names = ["R", "wait after R", "F (chain role)", "wait after F (chain)", "F (other role)", "wait after F (other)"]
+            per = dbg[:, :, :6].double().mean(dim=(0, 1)) * 2 / (L // 256)     # a warp has either role every second block
+            per[0] /= 2
+            per[1] /= 2
+            ms = e0.elapsed_time(e1)
+            print(json.dumps({"B": B, "ms": round(ms, 3), "cycles_per_block": round(ms * 1.965e6 / (L // 256)),
+                              "phases": {n: round(float(v)) for n, v in zip(names, per)}}), flush=True)
+            continue
         d = dbg[:, :, :10].double()
         per_frame = d.mean(dim=0) / frames               # [nw][10] cycles per frame
         tot = per_frame.sum(dim=1)
