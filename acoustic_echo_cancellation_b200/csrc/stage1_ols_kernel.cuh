@@ -36,8 +36,14 @@ namespace aec {
 struct OlsSmem {
     static constexpr size_t tile_bytes = size_t(4) * kTilePitch * sizeof(float2);   // X [2], Yhat / E, W_c
     static constexpr size_t blk_bytes = size_t(4 + 2) * 256 * sizeof(float);        // far-end ring [4][256], microphone [2][256]
-    __host__ __device__ static constexpr size_t total(int P) {
-        return tile_bytes + blk_bytes + (size_t(P) * 20 + 16 + 15) / 16 * 16 + 64;
+    // far-end history of the regular bins in shared memory (Kalman step and 16 partitions: the state does not fit the
+    // registers next to the transform's): [P slots][256 bins] float2, one column per thread and bin
+    __host__ __device__ static constexpr bool ring(int P, bool kalman) { return kalman || P >= 16; }
+    __host__ __device__ static constexpr size_t base(int P) {                            // + bin 128, ERLE partials, role word
+        return tile_bytes + blk_bytes + (size_t(P) * 20 + 16 + 15) / 16 * 16 + 128;
+    }
+    __host__ __device__ static constexpr size_t total(int P, bool kalman) {
+        return base(P) + (ring(P, kalman) ? size_t(P) * 256 * sizeof(float2) : 0);
     }
 };
 
@@ -95,10 +101,29 @@ __device__ __forceinline__ void ols_update(float2 (&W)[P], const float2 (&X)[P],
     for (int j = 0; j < P; ++j) W[j] = Wn[j];
 }
 
+// Shape of the CTA: every thread keeps 16 bin-taps of state (taps, far-end history, covariances) in registers, so the
+// number of warps grows with the filter: 1-4 partitions: 2 warps, two mirrored pairs (4 bins) per thread; 8 partitions:
+// 4 warps, one pair per thread; 16 partitions: 8 warps, ONE bin per thread (lanes 2i / 2i+1 share the mirrored pair i: both
+// do the split of the pair and keep their own bin, and swap their results by shuffle for the packing).  The transform
+// phase is the same for all of them (one warp carries the chain, one the far-end transforms); the roles rotate over all
+// warps of the CTA.
+template <int P>
+struct OlsShape {
+    static constexpr int NW = P <= 4 ? 2 : P / 2;
+    static constexpr int NT = 32 * NW;
+    static constexpr bool kSplit = (NW == 8);
+    static constexpr int PPT = kSplit ? 1 : 128 / NT;      // pair slots per thread
+    static constexpr int NB = kSplit ? 1 : 2 * PPT;        // bins per thread
+};
+
 template <int P, bool KAL, bool ECHO, int REGS>
-__global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const Stage1Params prm) {
-    static_assert(P == 1 || P == 2 || P == 4, "partitions: a power of two, in registers");
+__global__ void __launch_bounds__(OlsShape<P>::NT) __maxnreg__(REGS) stage1_ols_kernel(const Stage1Params prm) {
+    static_assert(P == 1 || P == 2 || P == 4 || P == 8 || P == 16, "partitions: a power of two, in registers");
+    using SH = OlsShape<P>;
+    constexpr int NW = SH::NW, NT = SH::NT, PPT = SH::PPT, NB = SH::NB;
+    constexpr bool kSplit = SH::kSplit;
     constexpr int PC = KAL ? P : 1;
+    constexpr bool kXs = OlsSmem::ring(P, KAL);                      // far-end history in shared memory instead of registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* tileX = reinterpret_cast<float2*>(smem_raw);             // [2] spectra of the far-end blocks, slot = block & 1
     float2* tileY = tileX + 2 * kTilePitch;
@@ -109,10 +134,12 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
     float2* midX = midW + P;                                         // [P] its far-end history, slot = block mod P
     float* midC = reinterpret_cast<float*>(midX + P);                // [P] covariances (Kalman)
     float* midS = midC + P;                                          // [1] smoothed power / Psi
-    float* red = midS + 1;                                           // [4] ERLE energies of the two warps
-    int* fft_warp_s = reinterpret_cast<int*>(red + 4);
+    float* red = midS + 1;                                           // [2 NW] ERLE energies of the warps
+    int* fft_warp_s = reinterpret_cast<int*>(red + 2 * NW);
+    float2* xhist = reinterpret_cast<float2*>(smem_raw + OlsSmem::base(P));   // [P][NB][NT] (kXs), slot = block mod P
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, h = lane & 15;
+    const int side = tid & 1;                                        // kSplit: 0 = bin k, 1 = bin 256 - k of pair k = tid >> 1
 
     long long n_ll = prm.n_samples ? prm.n_samples[blockIdx.x] : prm.L;
     n_ll = n_ll < 0 ? 0 : (n_ll > prm.L ? prm.L : n_ll);
@@ -122,14 +149,14 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
     float* err_b = prm.err + static_cast<long long>(blockIdx.x) * prm.out_stride;
     float* echo_b = ECHO ? prm.echo + static_cast<long long>(blockIdx.x) * prm.out_stride : nullptr;
 
-    // Warp w of a two-warp CTA always sits on scheduler (slot + w) % 4, and the warp that carries the two-transform
-    // chain is the busier one: which warp starts with it follows the hardware warp slot, so that co-resident utterances
-    // on the same scheduler pair load different schedulers (same device as the bin-128 owner of the STFT-domain kernel);
-    // the roles then swap every block.
+    // Warp w of a CTA sits on scheduler (slot + w) % 4, and the warp that carries the two-transform chain is the busier
+    // one.  The roles rotate over the warps every block; for the two-warp CTAs (which only ever touch one scheduler pair)
+    // the warp that starts with the chain follows the hardware warp slot, so that co-resident utterances on the same
+    // scheduler pair load different schedulers (same device as the bin-128 owner of the STFT-domain kernel).
     if (tid == 0) {
         unsigned hw_warp;
         asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
-        *fft_warp_s = static_cast<int>((hw_warp >> 2) & 1u);
+        *fft_warp_s = NW == 2 ? static_cast<int>((hw_warp >> 2) & 1u) : 0;
     }
     if (tid < P) {
         midW[tid] = make_float2(0.f, 0.f);
@@ -137,9 +164,11 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
         midC[tid] = prm.kc0;
     }
     if (tid == 0) *midS = 0.f;
-    for (int i = tid; i < 256; i += 64) xring[3 * 256 + i] = 0.f;    // x_{-1} = 0 (slot of block -1)
+    for (int i = tid; i < 256; i += NT) xring[3 * 256 + i] = 0.f;    // x_{-1} = 0 (slot of block -1)
+    if constexpr (kXs)
+        for (int i = tid; i < P * 256; i += NT) xhist[i] = make_float2(0.f, 0.f);
 #ifdef AEC_PHASE_TIMING
-    __shared__ long long dbg_sm[2][12];
+    __shared__ long long dbg_sm[NW][12];
     if (lane == 0) {
         for (int i = 0; i < 11; ++i) dbg_sm[warp][i] = 0;
         dbg_sm[warp][11] = clock64();
@@ -154,27 +183,27 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
     twr.w4 = __ldg(&prm.tw256[4 * 16 + h]);
     twr.w8 = __ldg(&prm.tw256[8 * 16 + h]);
 
-    // ---- persistent per-bin state: thread owns the mirrored pairs (k, 256 - k), k = tid, tid + 64 ----
-    float2 W[4][P], X[4][P];
-    float C[4][PC], sp[4];
-    float2 wk[2];
+    // ---- persistent per-bin state ----
+    float2 W[NB][P], Xp[kXs ? 1 : NB][kXs ? 1 : P];
+    float C[NB][PC], sp[NB];
+    float2 wk[PPT];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < NB; ++b) {
         sp[b] = 0.f;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             W[b][p] = make_float2(0.f, 0.f);
-            X[b][p] = make_float2(0.f, 0.f);
+            if constexpr (!kXs) Xp[b][p] = make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int p = 0; p < PC; ++p) C[b][p] = prm.kc0;
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) wk[i] = __ldg(&prm.tw512[tid + 64 * i]);
+    for (int i = 0; i < PPT; ++i) wk[i] = __ldg(&prm.tw512[kSplit ? (tid >> 1) : tid + NT * i]);
 
     // block staging: 64 threads x 4 samples per signal
     auto stage_block = [&](const float* row, float* dst, int blk) {
-        if (blk < nblk) {
+        if (blk < nblk && tid < 64) {
             const float* p = row + static_cast<long long>(blk) * 256 + 4 * tid;
             if (prm.use_tma) {
                 cp_async16(dst + 4 * tid, p);
@@ -194,43 +223,82 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
         stage_block(far_b, xring + ((t + 3) & 3) * 256, t + 3);
         stage_block(mic_b, dring + ((t + 1) & 1) * 256, t + 1);
         cp_async_commit();
-        const int a = (fw + t) & 1;                                   // the warp that carries the chain of this block
+        const int a = (fw + t) & (NW - 1);                            // the warp that carries the chain of this block
         // ---- R: update with E_{t-1}, echo estimate of block t ----
         if (t >= 0) {
             const int c = t & (P - 1);                                // partition constrained in this block = ring slot of X_t
             const float2* tX = tileX + (t & 1) * kTilePitch;
+            // far-end history of this thread's bins: the persistent registers, or (kXs) a copy of the thread's columns of
+            // the shared-memory ring that lives for this phase only
+            float2 Xl[kXs ? NB : 1][kXs ? P : 1];
+            float2 (&X)[NB][P] = *reinterpret_cast<float2 (*)[NB][P]>(kXs ? &Xl[0][0] : &Xp[0][0]);
+            if constexpr (kXs) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int k = tid + 64 * i, km = (256 - k) & 255;
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int s2 = 0; s2 < P; ++s2) X[b][s2] = xhist[(s2 * NB + b) * NT + tid];
+            }
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) {
+                const int k = kSplit ? (tid >> 1) : tid + NT * i, km = (256 - k) & 255;
+                const int b0 = kSplit ? 0 : 2 * i, b1 = kSplit ? 0 : 2 * i + 1;     // this thread's bins k / 256 - k
                 if (t >= 1) {
-                    float2 ek, em;
+                    float2 ek, em, ca, cb;
                     unpack_pair(tileY[k], tileY[km], wk[i], ek, em);
-                    unpack_pair(tileW[k], tileW[km], wk[i], W[2 * i][0], W[2 * i + 1][0]);   // the constrained partition
-                    ols_update<P, KAL, true>(W[2 * i], X[2 * i], C[2 * i], sp[2 * i], ek, prm);
-                    ols_update<P, KAL, true>(W[2 * i + 1], X[2 * i + 1], C[2 * i + 1], sp[2 * i + 1], em, prm);
+                    unpack_pair(tileW[k], tileW[km], wk[i], ca, cb);                    // the constrained partition
+                    if constexpr (kSplit) {
+                        W[0][0] = side ? cb : ca;
+                        ols_update<P, KAL, true>(W[0], X[0], C[0], sp[0], side ? em : ek, prm);
+                    } else {
+                        W[b0][0] = ca;
+                        W[b1][0] = cb;
+                        ols_update<P, KAL, true>(W[b0], X[b0], C[b0], sp[b0], ek, prm);
+                        ols_update<P, KAL, true>(W[b1], X[b1], C[b1], sp[b1], em, prm);
+                    }
                 }
                 float2 xk, xm, gk, gm;
                 unpack_pair(tX[k], tX[km], wk[i], xk, xm);
+                if constexpr (kSplit) xk = side ? xm : xk;
 #pragma unroll
                 for (int s = 0; s < P; ++s)
                     if (c == s) {
-                        X[2 * i][s] = xk;
-                        X[2 * i + 1][s] = xm;
+                        X[b0][s] = xk;
+                        if constexpr (!kSplit) X[b1][s] = xm;
                     }
-                float2 yk = make_float2(0.f, 0.f), ym = make_float2(0.f, 0.f);
+                if constexpr (kXs) {
+                    xhist[(c * NB + b0) * NT + tid] = xk;
+                    if constexpr (!kSplit) xhist[(c * NB + b1) * NT + tid] = xm;
+                }
+                float2 yk = make_float2(0.f, 0.f), ym = make_float2(0.f, 0.f), wa = W[b0][0], wb = W[b1][0];
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
-                    yk = cfma(W[2 * i][j], X[2 * i][(P - j) % P], yk);
-                    ym = cfma(W[2 * i + 1][j], X[2 * i + 1][(P - j) % P], ym);
+                    yk = cfma(W[b0][j], X[b0][(P - j) % P], yk);
+                    if constexpr (!kSplit) ym = cfma(W[b1][j], X[b1][(P - j) % P], ym);
+                }
+                if constexpr (kSplit) {          // the partner lane holds the other bin of the pair
+                    const float2 yo = make_float2(__shfl_xor_sync(0xffffffffu, yk.x, 1), __shfl_xor_sync(0xffffffffu, yk.y, 1));
+                    const float2 wo = make_float2(__shfl_xor_sync(0xffffffffu, wa.x, 1), __shfl_xor_sync(0xffffffffu, wa.y, 1));
+                    ym = side ? yk : yo;
+                    yk = side ? yo : yk;
+                    wb = side ? wa : wo;
+                    wa = side ? wo : wa;
                 }
                 pack_pair(yk, ym, wk[i], gk, gm);
-                tileY[k] = gk;
-                tileY[km] = gm;
-                pack_pair(W[2 * i][0], W[2 * i + 1][0], wk[i], gk, gm);
-                tileW[k] = gk;
-                tileW[km] = gm;
+                if constexpr (kSplit) {
+                    tileY[side ? km : k] = side ? gm : gk;
+                } else {
+                    tileY[k] = gk;
+                    tileY[km] = gm;
+                }
+                pack_pair(wa, wb, wk[i], gk, gm);
+                if constexpr (kSplit) {
+                    tileW[side ? km : k] = side ? gm : gk;
+                } else {
+                    tileW[k] = gk;
+                    tileW[km] = gm;
+                }
             }
-            if (tid == (a ^ 1) * 32 + 31) {                           // bin 128, on the warp with the lighter transform phase
+            if (tid == ((a + 1) & (NW - 1)) * 32 + 31) {              // bin 128, on a warp with a light transform phase
                 // its split / packing twiddle is -i: the real-signal bin is 2 conj(Z[128]), and back (exact, no multiplies)
                 auto conj2 = [](float2 z) { return make_float2(2.f * z.x, -2.f * z.y); };
                 float2 mw[P], mx[P];                                  // by partition / by delay (as of block t - 1)
@@ -275,9 +343,9 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
         cp_async_wait<1>();                                           // blocks staged one iteration ago have landed
         __syncthreads();
         AEC_TICK(1);                                                  // wait after R
-        // ---- F: the two transform slots of the chain on warp a; X_{t+1}, X_{t+2} on the other warp (odd t) ----
+        // ---- F: the two transform slots of the chain on warp a; X_{t+1}, X_{t+2} on another warp (odd t) ----
         const bool chain = (warp == a) && (t >= 0);
-        const bool xjob = (warp != a) && (t & 1) && (t + 1 < nblk);
+        const bool xjob = (warp == ((a + NW / 2) & (NW - 1))) && (t & 1) && (t + 1 < nblk);
         if (chain || xjob) {
             float2 v[16];
             float2* tile;
@@ -338,7 +406,7 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
             for (int p = 0; p < 16; ++p) tile[h + 16 * fft16_index(p)] = v[p];
         }
 #ifdef AEC_PHASE_TIMING
-        if (warp == a) AEC_TICK(2); else AEC_TICK(4);                 // F as the chain warp / as the other warp
+        if (warp == a) AEC_TICK(2); else AEC_TICK(4);                 // F as the chain warp / as another warp
 #endif
         __syncthreads();
 #ifdef AEC_PHASE_TIMING
@@ -348,7 +416,7 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
     cp_async_wait<0>();
 
     // ---- epilogue: zero the output beyond the last whole block, ERLE ----
-    for (long long i = static_cast<long long>(nblk) * 256 + tid; i < prm.out_stride && i < prm.L; i += 64) {
+    for (long long i = static_cast<long long>(nblk) * 256 + tid; i < prm.out_stride && i < prm.L; i += NT) {
         err_b[i] = 0.f;
         if constexpr (ECHO) echo_b[i] = 0.f;
     }
@@ -363,12 +431,18 @@ __global__ void __launch_bounds__(64) __maxnreg__(REGS) stage1_ols_kernel(const 
             red[2 * warp + 1] = acc_e;
         }
         __syncthreads();
-        if (tid == 0)
-            prm.erle_db[blockIdx.x] = 10.f * log10f(fmaxf(red[0] + red[2], 1e-20f) / fmaxf(red[1] + red[3], 1e-20f));
+        if (tid == 0) {
+            float m = 0.f, e = 0.f;
+            for (int w = 0; w < NW; ++w) {
+                m += red[2 * w];
+                e += red[2 * w + 1];
+            }
+            prm.erle_db[blockIdx.x] = 10.f * log10f(fmaxf(m, 1e-20f) / fmaxf(e, 1e-20f));
+        }
     }
 #ifdef AEC_PHASE_TIMING
     if (lane == 0 && prm.dbg)
-        for (int i = 0; i < 12; ++i) prm.dbg[((long long)blockIdx.x * 2 + warp) * 12 + i] = dbg_sm[warp][i];
+        for (int i = 0; i < 12; ++i) prm.dbg[((long long)blockIdx.x * NW + warp) * 12 + i] = dbg_sm[warp][i];
 #endif
 }
 

@@ -398,6 +398,8 @@ def also_rows(A, torch, sharding, args, fp32_peak, hbm_peak, hbm_src, local):
                                              "alternated constraint, NLMS step; ~38 dB ERLE where the STFT-domain filter "
                                              "reaches 13)"),
              dict(WORKLOADS[2], algo=3, name="configs[1] through the overlap-save PBFDAF with the Kalman step (algo 3)"),
+             dict(WORKLOADS[3], algo=3, name="configs[2] through the overlap-save PBFDAF with the Kalman step (algo 3, 16 "
+                                             "partitions, eight warps per utterance)"),
              dict(WORKLOADS[2], feat=True, name="configs[1] with the Stage-2 feature front end fused into the kernel "
                                                 "(aec_stage1_run_features: error signal + [B, T, 64] features per launch)")]
     for wl in extra:
