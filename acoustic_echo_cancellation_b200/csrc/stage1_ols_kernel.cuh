@@ -36,9 +36,12 @@ namespace aec {
 struct OlsSmem {
     static constexpr size_t tile_bytes = size_t(4) * kTilePitch * sizeof(float2);   // X [2], Yhat / E, W_c
     static constexpr size_t blk_bytes = size_t(4 + 2) * 256 * sizeof(float);        // far-end ring [4][256], microphone [2][256]
-    // far-end history of the regular bins in shared memory (Kalman step and 16 partitions: the state does not fit the
-    // registers next to the transform's): [P slots][256 bins] float2, one column per thread and bin
-    __host__ __device__ static constexpr bool ring(int P, bool kalman) { return kalman || P >= 16; }
+    // far-end history of the regular bins in shared memory: [P slots][256 bins] float2, one column per thread and bin,
+    // copied into registers for the update / estimate phase only.  With the Kalman step (and at 16 partitions) the state
+    // does not fit the registers next to the transform's 16 complex values (2.85 against 3.4 ms per 1024 x 10 s at P = 4);
+    // for the NLMS step it removes the last spills of the 128-register builds (2.30 against 2.38 ms at P = 4, 3.64 against
+    // 3.73 at P = 8); at 1 / 2 partitions the registers hold it for free.
+    __host__ __device__ static constexpr bool ring(int P, bool kalman) { return kalman || P >= 4; }
     __host__ __device__ static constexpr size_t base(int P) {                            // + bin 128, ERLE partials, role word
         return tile_bytes + blk_bytes + (size_t(P) * 20 + 16 + 15) / 16 * 16 + 128;
     }
