@@ -44,9 +44,12 @@ enum {
 };
 
 /* 0, 1: the STFT-domain recurrence (Hann-windowed STFT, one complex tap per bin and past hop) with an NLMS / Kalman step;
- * 2: overlap-save partitioned-block FDAF with the alternated gradient constraint -- time-domain blocks of hop new
- *    samples, FFT length frame, exact linear convolution (no analysis window; ~26 dB more ERLE on the single-talk set,
- *    DESIGN.md section 2); NLMS step on a smoothed input power.  Frame 512, partitions 1 / 2 / 4. */
+ * 2, 3: overlap-save partitioned-block FDAF with the alternated gradient constraint -- time-domain blocks of hop new
+ *    samples, FFT length frame, exact linear convolution (no analysis window; ~25 dB more ERLE on the single-talk set,
+ *    DESIGN.md section 2b).  2 = NLMS step on a smoothed input power (pb_lambda), 3 = the diagonal Kalman step of algo 1
+ *    (kalman_*; holds ~15 dB through double talk where the NLMS step drops to 2).  Frame 512, partitions 1 / 2 / 4 / 8 / 16;
+ *    outputs cover the whole blocks only ((n / hop) * hop samples, the same count as (frames - 1) * hop of algos 0 / 1);
+ *    no fused feature epilogue.  All four recurrences are builder-authored: the reference has no stage-1 filter. */
 enum { AEC_ALGO_NLMS = 0, AEC_ALGO_KALMAN = 1, AEC_ALGO_PBFDAF = 2, AEC_ALGO_PBFKF = 3 };
 
 /* Parameter block of the stage-1 filter.  frame / hop follow the reference's
@@ -55,7 +58,7 @@ enum { AEC_ALGO_NLMS = 0, AEC_ALGO_KALMAN = 1, AEC_ALGO_PBFDAF = 2, AEC_ALGO_PBF
 typedef struct aec_cfg {
     int32_t frame;          /* N: 512 (16 kHz) or 1024 (48 kHz) */
     int32_t partitions;     /* P: taps per bin, one per past hop */
-    int32_t algo;           /* AEC_ALGO_NLMS | AEC_ALGO_KALMAN */
+    int32_t algo;           /* AEC_ALGO_NLMS | AEC_ALGO_KALMAN | AEC_ALGO_PBFDAF | AEC_ALGO_PBFKF */
     float mu;               /* NLMS step size                      (default 0.5) */
     float delta;            /* NLMS regulariser                    (default 1e-6 * frame) */
     float kalman_a;         /* Kalman transition factor A          (default 0.999) */

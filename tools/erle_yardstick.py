@@ -30,10 +30,11 @@ def main():
     args = ap.parse_args()
     L = int(args.seconds * 16000)
     rows = []
-    for P, algo, name in [(4, O.ALGO_NLMS, "P=4 NLMS"), (4, O.ALGO_KALMAN, "P=4 Kalman"), (16, O.ALGO_KALMAN, "P=16 Kalman"),
-                          (16, O.ALGO_NLMS, "P=16 NLMS")]:
+    for P, algo, name in [(4, O.ALGO_NLMS, "P=4 NLMS"), (4, O.ALGO_KALMAN, "P=4 Kalman"), (8, O.ALGO_NLMS, "P=8 NLMS"),
+                          (8, O.ALGO_KALMAN, "P=8 Kalman"), (16, O.ALGO_KALMAN, "P=16 Kalman"), (16, O.ALGO_NLMS, "P=16 NLMS")]:
         for dt in (False, True):
-            acc = {"stft": [], "stft_dt": [], "pb": [], "pb_dt": [], "pb_unc": []}
+            acc = {"stft": [], "stft_dt": [], "pb": [], "pb_dt": [], "pb_unc": [], "algo2": [], "algo2_dt": [], "algo3": [],
+                   "algo3_dt": []}
             for u in range(args.utterances):
                 d = synth.make_utterance(u, L, rir_len=P * 256, double_talk=dt)
                 far, mic, echo = (d[k].astype(np.float64) for k in ("far", "mic", "echo"))
@@ -42,6 +43,20 @@ def main():
                 pe, py = pbfdaf(far, mic, P)
                 pu, _ = pbfdaf(far, mic, P, constrained=False)
                 n = min(len(e), len(pe))
+                # the product's overlap-save filters (algos 2 / 3: alternated constraint on the partition as it entered the
+                # block, NLMS step on a smoothed power / Kalman step) -- stated once per filter length, not per STFT step rule
+                for key, a2 in (("algo2", O.ALGO_PBFDAF), ("algo3", O.ALGO_PBFKF)):
+                    if algo != O.ALGO_NLMS:
+                        continue
+                    r2 = O.stage1(far[None], mic[None], O.AecConfig(partitions=P, algo=a2))
+                    e2, y2 = r2["err"][0], r2["echo"][0]
+                    if not dt:
+                        lo = int(0.4 * n)
+                        acc[key].append(db(mic[lo:n], e2[lo:n]))
+                    else:
+                        a, b = int(0.4 * L), int(0.7 * L)
+                        acc[key + "_dt"].append(db(echo[a:b], (echo[:n] - y2[:n])[a:b]))
+                        acc[key].append(db(echo[b:n], (echo[:n] - y2[:n])[b:n]))
                 if not dt:
                     lo = int(0.4 * n)
                     acc["stft"].append(db(mic[lo:n], e[lo:n]))

@@ -15,7 +15,7 @@ for B in [int(a) for a in sys.argv[1:]] or [1024, 4144]:
     far = 0.1 * torch.randn(B, L, device="cuda", generator=g)
     mic = 0.5 * torch.roll(far, 37, dims=1) + 0.001 * torch.randn(B, L, device="cuda", generator=g)
     out = torch.empty_like(far)
-    for algo, P, var in ((2, 1, 0), (2, 2, 0), (2, 4, 0), (3, 4, 0), (2, 8, 0), (3, 8, 0), (2, 16, 0), (3, 16, 0)):
+    for algo, P, var in ((0, 4, 0), (2, 1, 0), (2, 2, 0), (2, 4, 0), (3, 4, 0), (0, 8, 0), (2, 8, 0), (3, 8, 0), (1, 16, 0), (2, 16, 0), (3, 16, 0)):
         cfg = A.Stage1Config(partitions=P, algo=algo, erle_skip_hops=125, variant=var)
         for _ in range(3):
             A.stage1_aec(far, mic, cfg, out=out, return_erle=True)

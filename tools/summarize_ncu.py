@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--tag", required=True)
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--frames", type=int, default=1024 * 626, help="frames processed by the captured launch")
+    ap.add_argument("--traffic-key", default=None, help="key in profiles/traffic.json (default: config<N>)")
+    ap.add_argument("--step-args", default=None, help="arguments of tools/profile_step.py used for the capture")
     a = ap.parse_args()
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     lines = [f"# ncu summary `{a.tag}`", ""]
@@ -51,7 +53,7 @@ def main():
         hdr, units, vals = rows[0], rows[1], rows[2]
         d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
         lines += [f"kernel: `{d['Kernel Name'][1]}`  (capture: `ncu --set full --clock-control none --import-source on`, "
-                  f"one launch after 2 warm-up launches, `tools/profile_step.py --config {a.config}`)", "",
+                  f"one launch after 2 warm-up launches, `tools/profile_step.py {a.step_args or '--config ' + str(a.config)}`)", "",
                   "| metric | unit | value |", "|---|---|---|"]
         for k in KEYS:
             if k in d:
@@ -66,8 +68,9 @@ def main():
         wr = float(d["dram__bytes_write.sum"][1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[d["dram__bytes_write.sum"][0]]
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
-        traffic[f"config{a.config}"] = rd + wr
-        traffic[f"config{a.config}_source"] = f"{a.tag}: dram__bytes_read.sum + dram__bytes_write.sum of one launch"
+        tkey = a.traffic_key or f"config{a.config}"
+        traffic[tkey] = rd + wr
+        traffic[f"{tkey}_source"] = f"{a.tag}: dram__bytes_read.sum + dram__bytes_write.sum of one launch"
         json.dump(traffic, open(tpath, "w"), indent=1)
         lines += ["", f"DRAM traffic per launch: {rd + wr:.4g} B (read {rd:.4g} + write {wr:.4g})"]
         # per-phase breakdown from the SASS page (phases are delimited by BAR.SYNC)
