@@ -36,7 +36,7 @@ def main():
     setter = lib.aec_debug_set_phase_buffer
     setter.argtypes = [C.c_void_p]
     setter.restype = None
-    nw = args.variant // 1000 if args.algo < 2 else 2
+    nw = args.variant // 1000 if args.algo < 2 else (2 if args.partitions <= 4 else args.partitions // 2)
     L = args.samples
     frames = L // 256 + 1
     for B in [int(x) for x in args.batches.split(",")]:
@@ -58,9 +58,11 @@ def main():
         setter(None)
         if args.algo >= 2:      # overlap-save kernels: two phases per block, the warps swap roles every block
             names = ["R", "wait after R", "F (chain role)", "wait after F (chain)", "F (other role)", "wait after F (other)"]
-            per = dbg[:, :, :6].double().mean(dim=(0, 1)) * 2 / (L // 256)     # a warp has either role every second block
-            per[0] /= 2
-            per[1] /= 2
+            per = dbg[:, :, :6].double().sum(dim=1).mean(dim=0) / (L // 256)     # summed over the warps: cycles per block
+            per[0] /= nw                                                           # R: every warp, every block
+            per[1] /= nw
+            per[4] /= max(nw - 1, 1)                                               # the nw - 1 warps that do not carry the chain
+            per[5] /= max(nw - 1, 1)
             ms = e0.elapsed_time(e1)
             print(json.dumps({"B": B, "ms": round(ms, 3), "cycles_per_block": round(ms * 1.965e6 / (L // 256)),
                               "phases": {n: round(float(v)) for n, v in zip(names, per)}}), flush=True)
