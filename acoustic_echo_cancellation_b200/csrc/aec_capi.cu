@@ -13,7 +13,7 @@
 #include "aec_common.cuh"
 #include "stage1_launch.cuh"
 #include "stage1_kernel_1024.cuh"
-#include "stage1_ols_kernel.cuh"
+#include "stage1_ols1024_kernel.cuh"   // (includes stage1_ols_kernel.cuh) launchers of the overlap-save kernels
 
 namespace aec {
 
@@ -370,8 +370,12 @@ static int stage1_run_impl(const float* far, const float* mic, float* err, float
     }
     cudaError_t e;
     if (cfg->algo == AEC_ALGO_PBFDAF || cfg->algo == AEC_ALGO_PBFKF) {
-        if (feat || wide) return AEC_EUNSUPPORTED;       // frame 512, no fused features for the overlap-save filters
-        e = launch_stage1_ols(P, cfg->algo == AEC_ALGO_PBFKF, echo, cfg->variant > 0 ? cfg->variant % 1000 : 0, p, s);
+        if (feat) return AEC_EUNSUPPORTED;               // no fused features for the overlap-save filters
+        if (wide) {
+            if (cfg->variant > 0) return AEC_EUNSUPPORTED;
+            e = launch_stage1_ols1024(P, cfg->algo == AEC_ALGO_PBFKF, echo, p, s);
+        } else
+            e = launch_stage1_ols(P, cfg->algo == AEC_ALGO_PBFKF, echo, cfg->variant > 0 ? cfg->variant % 1000 : 0, p, s);
     } else if (feat) {
         e = launch_stage1_feat(P, cfg->algo, p, s);
     } else if (wide) {

@@ -337,7 +337,8 @@ def roofline_of(wl, kern_ms, fp32_peak, hbm_peak, hbm_src, traffic=None):
     tf = flops_launch / (kern_ms * 1e-3) / 1e12
     gbs = bytes_launch / (kern_ms * 1e-3) / 1e9
     return {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
-            "traffic": traffic, "kernel": "aec::stage1_n%d_kernel" % wl["frame"] if wl["algo"] < 2 else "aec::stage1_ols_kernel",
+            "traffic": traffic, "kernel": "aec::stage1_n%d_kernel" % wl["frame"] if wl["algo"] < 2 else
+            ("aec::stage1_ols_kernel" if wl["frame"] == 512 else "aec::stage1_ols1024_kernel"),
             "kernel_ms": kern_ms,
             "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
             "peak_source": "FFMA probe measured live in this run (aec_bench_fp32_peak; FFMAs with constant operands -- "
@@ -400,6 +401,8 @@ def also_rows(A, torch, sharding, args, fp32_peak, hbm_peak, hbm_src, local):
              dict(WORKLOADS[2], algo=3, name="configs[1] through the overlap-save PBFDAF with the Kalman step (algo 3)"),
              dict(WORKLOADS[3], algo=3, name="configs[2] through the overlap-save PBFDAF with the Kalman step (algo 3, 16 "
                                              "partitions, eight warps per utterance)"),
+             dict(WORKLOADS[4], algo=3, name="configs[3] through the overlap-save PBFDAF with the Kalman step (algo 3, frame 1024, 8 "
+                                             "partitions: the double-talk configuration through the double-talk-robust filter)"),
              dict(WORKLOADS[2], feat=True, name="configs[1] with the Stage-2 feature front end fused into the kernel "
                                                 "(aec_stage1_run_features: error signal + [B, T, 64] features per launch)")]
     for wl in extra:

@@ -47,7 +47,8 @@ enum {
  * 2, 3: overlap-save partitioned-block FDAF with the alternated gradient constraint -- time-domain blocks of hop new
  *    samples, FFT length frame, exact linear convolution (no analysis window; ~25 dB more ERLE on the single-talk set,
  *    DESIGN.md section 2b).  2 = NLMS step on a smoothed input power (pb_lambda), 3 = the diagonal Kalman step of algo 1
- *    (kalman_*; holds ~15 dB through double talk where the NLMS step drops to 2).  Frame 512, partitions 1 / 2 / 4 / 8 / 16;
+ *    (kalman_*; holds ~15 dB through double talk where the NLMS step drops to 2).  Frame 512: partitions 1 / 2 / 4 / 8 / 16;
+ *    frame 1024: partitions 4 / 8;
  *    outputs cover the whole blocks only ((n / hop) * hop samples, the same count as (frames - 1) * hop of algos 0 / 1);
  *    no fused feature epilogue.  All four recurrences are builder-authored: the reference has no stage-1 filter. */
 enum { AEC_ALGO_NLMS = 0, AEC_ALGO_KALMAN = 1, AEC_ALGO_PBFDAF = 2, AEC_ALGO_PBFKF = 3 };

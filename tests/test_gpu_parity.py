@@ -85,6 +85,17 @@ def test_config4_48khz_double_talk_10s():
     _run_case(8, 0, 480000, B=2, double_talk=True, frame=1024, echo=False)
 
 
+@pytest.mark.parametrize("P,algo", [(8, 2), (8, 3), (4, 2), (4, 3)])
+def test_frame_1024_overlap_save_matches_oracle(P, algo):
+    """the overlap-save filters at the configs[3] geometry (blocks of 512 samples, FFT 1024): ragged lengths, echo estimate"""
+    _run_case(P, algo, 24000 + 77, ragged=True, B=4, frame=1024)
+
+
+def test_config4_48khz_double_talk_10s_overlap_save_kalman():
+    """configs[3] as worded (48 kHz, frame 1024, 8 partitions, double-talk mixes) through algo 3, 10 s"""
+    _run_case(8, 3, 480000, B=2, double_talk=True, frame=1024)
+
+
 def test_double_talk_mixes():
     _run_case(4, 0, 32000, double_talk=True)
     _run_case(4, 1, 32000, double_talk=True)
@@ -225,10 +236,11 @@ def test_wav2h5_runner_pcm16_and_tapered_slices_match_the_device_path():
     assert np.array_equal(err_f, dev[0].cpu().numpy()) and np.array_equal(echo_f, dev[1].cpu().numpy())
 
 
-def test_host_buffer_entry_matches_device_entry():
+@pytest.mark.parametrize("algo,P", [(0, 4), (3, 4), (2, 8)])
+def test_host_buffer_entry_matches_device_entry(algo, P):
     L, B = 16000, 10
     d = synth.make_batch(0, B, L)
-    cfg = A.Stage1Config(erle_skip_hops=4)
+    cfg = A.Stage1Config(erle_skip_hops=4, algo=algo, partitions=P)
     dev, dev_erle = A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg, return_erle=True)
     pipe = A.HostPipeline(slice_utterances=4, max_samples=L)          # 3 slices, last one partial
     err = np.empty((B, L), dtype=np.float32)
@@ -517,6 +529,15 @@ def test_unsupported_combination_is_reported_not_emulated():
     d = synth.make_batch(0, 1, 4096)
     with pytest.raises(A.AecError) as ei:
         A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), A.Stage1Config(partitions=5))
+    assert ei.value.code == -2
+    for cfg in (A.Stage1Config(partitions=3, algo=A.ALGO_PBFDAF),            # overlap-save: powers of two up to 16
+                A.Stage1Config(partitions=16, algo=A.ALGO_PBFKF, frame=1024)):  # ... frame 1024: 4 or 8 partitions
+        with pytest.raises(A.AecError) as ei:
+            A.stage1_aec(_cuda(d["far"]), _cuda(d["mic"]), cfg)
+        assert ei.value.code == -2
+    with pytest.raises(A.AecError) as ei:                                       # no fused feature epilogue for them
+        A.stage1_aec_features(_cuda(d["far"]), _cuda(d["mic"]), torch.from_numpy(A.erb_filterbank()).float().cuda(),
+                              A.Stage1Config(algo=A.ALGO_PBFDAF))
     assert ei.value.code == -2
 
 
