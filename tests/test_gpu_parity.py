@@ -432,6 +432,28 @@ def test_fused_feature_epilogue_ragged_rows_and_golden_front_end(golden):
     assert float((f - want).abs().max()) <= 2e-5 * max(float(want.abs().max()), 1.0)
 
 
+@pytest.mark.parametrize("B,P,algo,frame", [(1024, 4, 2, 512), (1024, 4, 3, 512), (2048, 16, 3, 512), (512, 8, 3, 1024)])
+def test_overlap_save_full_batches_against_the_oracle_on_random_utterances(B, P, algo, frame):
+    """full-occupancy batches (every SM holds its maximum of co-resident utterances) through the overlap-save kernels: 12
+    randomly chosen utterances of the batch against the float64 numpy oracle, 10 s each"""
+    rng = np.random.default_rng(17)
+    hop = frame // 2
+    L = 160000 * frame // 512
+    base = synth.make_batch(600, 8, L, sample_rate=16000 * frame // 512, rir_len=min(P * hop, 4096))
+    gains = (0.25 + 0.75 * rng.random(B)).astype(np.float32)
+    idx = torch.arange(B, device="cuda") % 8
+    far = torch.from_numpy(base["far"]).cuda()[idx] * torch.from_numpy(gains).cuda()[:, None]
+    mic = torch.from_numpy(base["mic"]).cuda()[idx] * torch.from_numpy(gains).cuda()[:, None]
+    cfg = A.Stage1Config(frame=frame, partitions=P, algo=algo, erle_skip_hops=125)
+    err, erle = A.stage1_aec(far, mic, cfg, return_erle=True)
+    pick = np.sort(rng.choice(B, size=12, replace=False))
+    ref = O.stage1(far[pick].cpu().numpy(), mic[pick].cpu().numpy(),
+                   O.AecConfig(frame=frame, partitions=P, algo=algo, delta=1e-6 * frame), erle_skip=125 * hop)
+    n = ref["err"].shape[1]
+    assert np.abs(err[pick].cpu().numpy()[:, :n] - ref["err"]).max() <= TOL_ERR
+    assert np.abs(erle[pick].cpu().numpy() - ref["erle_db"]).max() <= TOL_ERLE
+
+
 @pytest.mark.parametrize("algo", [2, 3])
 @pytest.mark.parametrize("P,L,B", [(4, 16000 + 123, 3), (2, 8 * 256, 2), (1, 4097, 2), (4, 300, 2), (4, 160000, 2),
                                    (8, 16000 + 123, 3), (16, 24000 + 5, 3), (8, 160000, 1), (16, 160000, 1)])
