@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(Ols1024Shape<P>::NT) __maxnreg__(REGS) stage1_
                 tileW[k] = gk;
                 tileW[km] = gm;
             }
+            if constexpr (KAL && P >= 8) {                            // bin 256, one lane per tap (8-partition Kalman step)
+                if (warp == ((a + 3) & (NW - 1)) && lane < P)
+                    ols_mid_parallel<P, KAL>(lane, t, midW, midX, midC, midS, tileY + 256, tileW + 256, tileX + 256, prm);
+            } else
             if (tid == ((a + 3) & (NW - 1)) * 32 + 31) {              // bin 256, on a warp without a transform
                 auto conj2 = [](float2 z) { return make_float2(2.f * z.x, -2.f * z.y); };   // split / packing twiddle -i
                 float2 mw[P], mx[P];                                  // by partition / by delay (as of block t - 1)

@@ -104,6 +104,58 @@ __device__ __forceinline__ void ols_update(float2 (&W)[P], const float2 (&X)[P],
     for (int j = 0; j < P; ++j) W[j] = Wn[j];
 }
 
+// The self-mirrored bin (128 at frame 512, 256 at frame 1024) for LONG filters, one lane per tap: lanes 0 .. P-1 of one
+// warp (P = 8 / 16), state in shared memory.  The serial form (one lane, all taps) is on the critical path of the update
+// phase -- ~600 cycles of a 16-tap Kalman step -- and its unrolled code is a tenth of the hot loop; this one is ~100
+// instructions and a few shuffle reductions.  zY / zW / zX: the bin's entries of the E / W_c / X tiles (split and packing
+// twiddle -i: the real-signal bin is 2 conj(Z), and back).
+template <int P, bool KAL>
+__device__ __forceinline__ void ols_mid_parallel(int p, int t, float2* midW, float2* midX, float* midC, float* midS, float2* zY,
+                                                 float2* zW, const float2* zX, const Stage1Params& prm) {
+    constexpr unsigned mask = P >= 32 ? 0xffffffffu : ((1u << P) - 1u);
+    auto conj2 = [](float2 z) { return make_float2(2.f * z.x, -2.f * z.y); };
+    auto sum = [&](float v) {
+#pragma unroll
+        for (int o = P / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+        return v;
+    };
+    const int c = t & (P - 1);
+    float2 w = midW[p];
+    float cc = KAL ? midC[p] : 0.f;
+    const float2 xo = midX[(t - 1 - p) & (P - 1)];                   // partner of partition p in block t - 1
+    __syncwarp(mask);                                                 // every lane has its X before slot c is overwritten
+    if (t >= 1) {
+        const float2 ek = conj2(*zY), ca = conj2(*zW);
+        if (p == ((t - 1) & (P - 1))) w = ca;                         // the constrained partition
+        const float x2 = fmaf(xo.x, xo.x, xo.y * xo.y);
+        if constexpr (!KAL) {
+            const float pw = fmaf(prm.pblam, *midS, prm.pboml * sum(x2));
+            const float g = prm.mu * rcp_fast(pw + prm.delta);
+            w = cfmac(xo, make_float2(g * ek.x, g * ek.y), w);
+            __syncwarp(mask);
+            if (p == 0) *midS = pw;
+        } else {
+            const float psi = fmaf(prm.klam, *midS, prm.koml * fmaf(ek.x, ek.x, ek.y * ek.y));
+            const float rd = __frcp_rn(sum(cc * x2) + psi + prm.keps);
+            const float gs = cc * rd;
+            w = cfma(make_float2(gs * xo.x, -gs * xo.y), ek, w);
+            w = make_float2(prm.ka * w.x, prm.ka * w.y);
+            cc = fmaf(prm.ka2 * (1.f - gs * x2), cc, prm.kq * fmaf(w.x, w.x, w.y * w.y));
+            midC[p] = cc;
+            __syncwarp(mask);
+            if (p == 0) *midS = psi;
+        }
+        midW[p] = w;
+    }
+    const float2 xk = conj2(*zX);
+    if (p == 0) midX[c] = xk;
+    const float2 xe = p == 0 ? xk : midX[(t - p) & (P - 1)];          // partner of partition p in block t
+    const float2 yp = cmul(w, xe);
+    const float2 y = make_float2(sum(yp.x), sum(yp.y));
+    if (p == 0) *zY = conj2(y);
+    if (p == c) *zW = conj2(w);
+}
+
 // Shape of the CTA: every thread keeps 16 bin-taps of state (taps, far-end history, covariances) in registers, so the
 // number of warps grows with the filter: 1-4 partitions: 2 warps, two mirrored pairs (4 bins) per thread; 8 partitions:
 // 4 warps, one pair per thread; 16 partitions: 8 warps, ONE bin per thread (lanes 2i / 2i+1 share the mirrored pair i: both
@@ -301,6 +353,10 @@ __global__ void __launch_bounds__(OlsShape<P>::NT) __maxnreg__(REGS) stage1_ols_
                     tileW[km] = gm;
                 }
             }
+            if constexpr (P >= 16 || (KAL && P >= 8)) {               // bin 128, one lane per tap (long filters)
+                if (warp == ((a + 1) & (NW - 1)) && lane < P)
+                    ols_mid_parallel<P, KAL>(lane, t, midW, midX, midC, midS, tileY + 128, tileW + 128, tX + 128, prm);
+            } else
             if (tid == ((a + 1) & (NW - 1)) * 32 + 31) {              // bin 128, on a warp with a light transform phase
                 // its split / packing twiddle is -i: the real-signal bin is 2 conj(Z[128]), and back (exact, no multiplies)
                 auto conj2 = [](float2 z) { return make_float2(2.f * z.x, -2.f * z.y); };
