@@ -142,6 +142,18 @@ __device__ __forceinline__ void st_stream_f2(float* p, float2 v) {
 __device__ __forceinline__ void st_stream_f1(float* p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// predicated forms: a store that only part of a warp performs, without a divergent branch around it (eight
+// BSSY / BRA / BSYNC regions in the overlap-save kernels' transform chain cost ~40 cycles of branch resolution each)
+__device__ __forceinline__ void st_stream_f2_if(float* p, float2 v, bool on) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n@q st.global.cs.v2.f32 [%0], {%1, %2};\n}" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "r"(static_cast<unsigned>(on))
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_f1_if(float* p, float v, bool on) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.global.cs.f32 [%0], %1;\n}" ::"l"(p), "f"(v),
+                 "r"(static_cast<unsigned>(on))
+                 : "memory");
+}
 
 // MUFU.RCP without the range fix-up code of __fdividef / the Newton step of 1.0f / x (the argument
 // is a regularised power, far from the denormal / overflow ranges; 1 ulp is ample for 1e-4 parity)

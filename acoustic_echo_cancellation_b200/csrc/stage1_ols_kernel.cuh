@@ -421,20 +421,23 @@ __global__ void __launch_bounds__(OlsShape<P>::NT) __maxnreg__(REGS) stage1_ols_
                 for (int p = 0; p < 16; ++p) u[fft16_index(p)] = v[p];
                 const float* dsrc = dring + (t & 1) * 256 + 2 * h;
                 const float sg = half == 0 ? 0.f : 0.5f * k512;
+                const bool st_v = half == 0 && prm.vec_out, st_s = half == 0 && !prm.vec_out;
                 float em = 0.f, ee = 0.f;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const float2 y = make_float2(u[8 + r].x * k512, u[8 + r].y * k512);
                     const float2 d = *reinterpret_cast<const float2*>(dsrc + 32 * r);
                     const float2 e = make_float2(d.x - y.x, d.y - y.y);
-                    if (half == 0) {
+                    {   // lower half-warp only: predicated stores, no divergent branch
                         float* dst = err_b + static_cast<long long>(t) * 256 + 2 * h + 32 * r;
-                        if (prm.vec_out) st_stream_f2(dst, e);
-                        else { st_stream_f1(dst, e.x); st_stream_f1(dst + 1, e.y); }
+                        st_stream_f2_if(dst, e, st_v);
+                        st_stream_f1_if(dst, e.x, st_s);
+                        st_stream_f1_if(dst + 1, e.y, st_s);
                         if constexpr (ECHO) {
                             float* dy = echo_b + static_cast<long long>(t) * 256 + 2 * h + 32 * r;
-                            if (prm.vec_out) st_stream_f2(dy, y);
-                            else { st_stream_f1(dy, y.x); st_stream_f1(dy + 1, y.y); }
+                            st_stream_f2_if(dy, y, st_v);
+                            st_stream_f1_if(dy, y.x, st_s);
+                            st_stream_f1_if(dy + 1, y.y, st_s);
                         }
                     }
                     em = fmaf(d.x, d.x, fmaf(d.y, d.y, em));

@@ -565,7 +565,7 @@ def main():
         he2 = A.pinned_empty((B, L))
         herle2 = np.empty(B, dtype=np.float32)
 
-        def time_host(a, b, streaming=False):
+        def time_host(a, b, streaming=False, cfg=cfg):
             """K steps through the host entry.  streaming: the steps are issued back to back in the context's deferred
             mode (a call returns once its last slice is enqueued; outputs alternate between two buffers) and ONE wait
             at the end of the timed region completes them -- every copy and kernel of every step is inside the region."""
@@ -607,6 +607,18 @@ def main():
         e2e_match = bool(np.array_equal(he, he16))
         hf[:] = far.cpu().numpy()
         hm[:] = mic.cpu().numpy()
+        # the same end-to-end call through the overlap-save filter with the Kalman step (algo 3): the kernel is 2x the
+        # time of the headline's, the step is the same -- the host link, not the filter, sets the end-to-end rate
+        ols_variant = None
+        if wl["frame"] == 512 and wl["P"] <= 16:
+            try:
+                cfg3 = A.Stage1Config(frame=wl["frame"], partitions=wl["P"], algo=3, erle_skip_hops=125)
+                dt16_ols = time_host(h16f, h16m, cfg=cfg3)
+                ols_variant = {"value": audio_s_step / dt16_ols, "unit": "audio-s/s", "ms_per_step": dt16_ols * 1e3,
+                               "algo": "ols-kalman (aec_cfg.algo = 3), same PCM16 host entry, per call",
+                               "outputs_finite": bool(np.isfinite(he).all())}
+            except Exception as e:                              # never lose the headline to a side measurement
+                ols_variant = {"error": repr(e)}
         e2e = {"value": audio_s_step / dt16_sync, "unit": "audio-s/s",
                "h2d_bytes_per_step": 2 * B * L * 2, "d2h_bytes_per_step": B * L * 4 + B * 4,
                "ms_per_step": dt16_sync * 1e3, "steps": k_e2e, "per_gpu": audio_s_step / dt16_sync / world,
@@ -619,7 +631,7 @@ def main():
                                      "equals_per_call": stream_match,
                                      "note": "the K steps issued back to back in the context's deferred mode "
                                              "(aec_host_ctx_set_deferred), one aec_host_ctx_wait inside the timed region"},
-               "float32_variant": f32_variant}
+               "float32_variant": f32_variant, "overlap_save_kalman_variant": ols_variant}
         pipe.close()
 
     if rank != 0:
