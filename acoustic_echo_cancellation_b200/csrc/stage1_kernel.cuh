@@ -282,6 +282,10 @@ __device__ __forceinline__ void pack_pair(float2 ek, float2 em, float2 w, float2
     gm = make_float2(a.x + t.y, t.x - a.y);
 }
 
+// The self-mirrored bin (k = N/4 on the half-size spectrum) has the split / packing twiddle -i, for which unpack_pair /
+// pack_pair reduce to 2 conj(.) -- the same values, without their multiplies by 0 and -1.
+__device__ __forceinline__ float2 mid_conj2(float2 z) { return make_float2(2.f * z.x, -2.f * z.y); }
+
 constexpr int kRingPitch = 256;   // far-end history ring: one float2 column per thread and slot (bin 128 has its own history);
                                   // a power of two, so that a slot offset is a shift instead of an integer multiply
 
@@ -605,7 +609,6 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         st_mid.init(prm.kc0);
         st_mid.store(mid_state);
     }
-    const float2 w_mid = make_float2(0.f, -1.f);
 
     // ---- bin 128 of the chunk starting at frame tc0, run by warps F/2 .. NW-1 (ring kernels) --------
     // step 1 (all four warps, two frames each): X[128], Y[128] straight from the staged samples;
@@ -913,14 +916,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
         if constexpr (kMidAhead) {
             // entries 128 of the tiles (no pair slot touches them): E / Yhat of bin 128, computed one chunk ahead
             if (tid < F && t0 + tid < T) {
-                float2 gk, gm;
                 const float2 e = midE[2 * tid], yh = midE[2 * tid + 1];
-                pack_pair(e, e, w_mid, gk, gm);
-                zbuf[(tid * 2 + 0) * kTilePitch + 128] = gk;
-                if constexpr (ECHO) {
-                    pack_pair(yh, yh, w_mid, gk, gm);
-                    zbuf[(tid * 2 + 1) * kTilePitch + 128] = gk;
-                }
+                zbuf[(tid * 2 + 0) * kTilePitch + 128] = mid_conj2(e);
+                if constexpr (ECHO) zbuf[(tid * 2 + 1) * kTilePitch + 128] = mid_conj2(yh);
             }
         }
         // (frame loop deliberately NOT unrolled: the chunk loop is ~30 KB of executed SASS against a 32 KB
@@ -988,21 +986,17 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     // self-mirrored bin 128, serial on the last lane of the owning warp (owner re-read from shared
                     // memory: a register live across the chunk loop tips the 128-register build into spilling)
                     if (tid == *static_cast<volatile int*>(mid_owner) * 32 + 31) {
-                        float2 xk, xm, yk, ym, ek, hk, gk, gm;
-                        const float2 fa = zf[128], ma = zm[128];
-                        unpack_pair(fa, fa, w_mid, xk, xm);
-                        unpack_pair(ma, ma, w_mid, yk, ym);
+                        // (split / packing twiddle of this bin is -i: the real-signal bin is 2 conj(Z[128]) and back -- the
+                        //  same values as unpack_pair / pack_pair produce, without their multiplies by 0 and -1)
+                        float2 ek, hk;
+                        const float2 xk = mid_conj2(zf[128]), yk = mid_conj2(zm[128]);
                         if constexpr (FEAT) f_magX[tl * kMagPitch + 128] = sqrt_approx(fmaf(xk.x, xk.x, fmaf(xk.y, xk.y, 1e-9f)));
                         BinState<P, ALGO> st_mid;
                         st_mid.load(mid_state);
                         bin_step<P, ALGO>(st_mid, xk, yk, prm, ek, hk);
                         st_mid.store(mid_state);
-                        pack_pair(ek, ek, w_mid, gk, gm);
-                        zf[128] = gk;
-                        if constexpr (ECHO) {
-                            pack_pair(hk, hk, w_mid, gk, gm);
-                            zm[128] = gk;
-                        }
+                        zf[128] = mid_conj2(ek);
+                        if constexpr (ECHO) zm[128] = mid_conj2(hk);
                     }
                 }
             }
@@ -1026,9 +1020,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                     if (t0 + tl < T) {
                         float2* zf = zbuf + (tl * 2 + 0) * kTilePitch;
                         float2* zm = zbuf + (tl * 2 + 1) * kTilePitch;
-                        float2 xn, yn, unused;
-                        unpack_pair(zf[128], zf[128], w_mid, xn, unused);
-                        unpack_pair(zm[128], zm[128], w_mid, yn, unused);
+                        const float2 xn = mid_conj2(zf[128]), yn = mid_conj2(zm[128]);
                         // tap p sees the spectrum tap p-1 saw one frame ago
                         float2 x = make_float2(__shfl_up_sync(0xffffffffu, xp.x, 1), __shfl_up_sync(0xffffffffu, xp.y, 1));
                         if (lane == 0) x = xn;
@@ -1050,13 +1042,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS) stage1_n512_kernel(
                         }
                         xp = x;
                         if (lane == 0) {
-                            float2 gk, gm;
-                            pack_pair(e, e, w_mid, gk, gm);
-                            zf[128] = gk;
-                            if constexpr (ECHO) {
-                                pack_pair(yh, yh, w_mid, gk, gm);
-                                zm[128] = gk;
-                            }
+                            zf[128] = mid_conj2(e);
+                            if constexpr (ECHO) zm[128] = mid_conj2(yh);
                         }
                     }
                 }

@@ -115,7 +115,6 @@ __global__ void __launch_bounds__(256) __maxnreg__(REGS) stage1_n1024_kernel(con
     st[0].init(prm.kc0);
     st[1].init(prm.kc0);
     const float2 wk = __ldg(&prm.tw512[tid]);
-    const float2 w_mid = make_float2(0.f, -1.f);
     if (tid == NT - 1) {
         BinState<P, ALGO> st_mid;
         st_mid.init(prm.kc0);
@@ -181,19 +180,14 @@ __global__ void __launch_bounds__(256) __maxnreg__(REGS) stage1_n1024_kernel(con
                     zm[km] = gm;
                 }
                 if (tid == NT - 1) {         // self-mirrored bin 256
-                    const float2 fa = zf[256], ma = zm[256];
-                    unpack_pair(fa, fa, w_mid, xk, xm);
-                    unpack_pair(ma, ma, w_mid, yk, ym);
+                    xk = mid_conj2(zf[256]);
+                    yk = mid_conj2(zm[256]);
                     BinState<P, ALGO> st_mid;
                     st_mid.load(mid_state);
                     bin_step<P, ALGO>(st_mid, xk, yk, prm, ek, hk);
                     st_mid.store(mid_state);
-                    pack_pair(ek, ek, w_mid, gk, gm);
-                    zf[256] = gk;
-                    if constexpr (ECHO) {
-                        pack_pair(hk, hk, w_mid, gk, gm);
-                        zm[256] = gk;
-                    }
+                    zf[256] = mid_conj2(ek);
+                    if constexpr (ECHO) zm[256] = mid_conj2(hk);
                 }
             }
         }
