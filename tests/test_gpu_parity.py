@@ -325,9 +325,11 @@ def test_runner_buffers_are_page_locked_and_pageable_inputs_are_staged():
     run.close()
 
 
-def test_create_h5_train_end_to_end_on_the_gpu(tmp_path):
+@pytest.mark.parametrize("algo_flag", [None, "ols-kalman"])
+def test_create_h5_train_end_to_end_on_the_gpu(tmp_path, algo_flag):
     """wav files -> create_h5 (decode | stage 1 | write, default CUDA runner, NpzStore container) -> files whose
-    stage-1 datasets are the device path's output on the decoded signals"""
+    stage-1 datasets are the device path's output on the decoded signals; with --stage1_algo ols-kalman the runner the
+    command-line flags build (wav2h5.runner_from_args) puts the overlap-save filter with the Kalman step there"""
     import types
 
     from scipy.io import wavfile
@@ -346,9 +348,15 @@ def test_create_h5_train_end_to_end_on_the_gpu(tmp_path):
             sig[(i, key)] = pcm.astype(np.float32) / np.float32(32768)
     args = types.SimpleNamespace(train_path=str(wav_dir), h5_path=str(h5_dir), list_path=str(list_dir), sr=16000)
     st = {}
-    paths = wav2h5.create_h5(args, batch=8, h5=wav2h5.NpzStore(), stats=st)
-    assert len(paths) == 37 and st["pcm16_batches"] == 5 and st["float32_batches"] == 0
     cfg = A.Stage1Config()
+    kw = {}
+    if algo_flag:
+        a = wav2h5.build_parser("train").parse_args(["--train_path", str(wav_dir), "--h5_path", str(h5_dir), "--list_path",
+                                                     str(list_dir), "--stage1_algo", algo_flag, "--stage1_partitions", "4"])
+        kw["runner"] = wav2h5.runner_from_args(a)
+        cfg = A.Stage1Config(algo=A.ALGO_PBFKF, partitions=4)
+    paths = wav2h5.create_h5(args, batch=8, h5=wav2h5.NpzStore(), stats=st, **kw)
+    assert len(paths) == 37 and st["pcm16_batches"] == 5 and st["float32_batches"] == 0
     for p in paths[::6]:
         i = p.split("tr_")[-1][:-3]
         with np.load(p) as z:
@@ -503,6 +511,29 @@ def test_overlap_save_unaligned_rows_and_batch_invariance(algo, P):
     assert torch.equal(odd, base)
     one = A.stage1_aec(far[3:4].contiguous(), mic[3:4].contiguous(), cfg)
     assert torch.equal(one[0], base[3])
+
+
+@pytest.mark.parametrize("algo,P,frame", [(2, 4, 512), (3, 4, 512), (3, 16, 512), (3, 8, 1024)])
+def test_overlap_save_oracle_free_properties(algo, P, frame):
+    """silent far end: the canceller is the identity, bit for bit (y = IFFT(0)); digital silence everywhere: zeros and a
+    finite ERLE (the regularisers); e + y = d to rounding; a 60 s utterance stays finite and converged"""
+    sr = 16000 * frame // 512
+    hop = frame // 2
+    d = synth.make_batch(40, 3, 6 * sr + 37, sample_rate=sr, rir_len=min(P * hop, 4096))
+    cfg = A.Stage1Config(frame=frame, partitions=P, algo=algo, erle_skip_hops=4)
+    mic = _cuda(d["mic"])
+    n = (mic.shape[1] // hop) * hop
+    err, echo = A.stage1_aec(torch.zeros_like(mic), mic, cfg, return_echo=True)
+    assert torch.equal(err[:, :n], mic[:, :n]) and not bool(echo.any())
+    err, echo, erle = A.stage1_aec(torch.zeros_like(mic), torch.zeros_like(mic), cfg, return_echo=True, return_erle=True)
+    assert not bool(err.any()) and not bool(echo.any()) and bool(torch.isfinite(erle).all())
+    err, echo = A.stage1_aec(_cuda(d["far"]), mic, cfg, return_echo=True)
+    assert float((err + echo - mic)[:, :n].abs().max()) <= 1e-6
+    long = synth.make_batch(41, 1, 60 * sr, sample_rate=sr, rir_len=min(P * hop, 4096))
+    e60, erle60 = A.stage1_aec(_cuda(long["far"]), _cuda(long["mic"]), A.Stage1Config(frame=frame, partitions=P, algo=algo,
+                                                                                     erle_skip_hops=30 * sr // hop),
+                               return_erle=True)
+    assert bool(torch.isfinite(e60).all()) and float(erle60[0]) > 25.0
 
 
 def test_overlap_save_pbfdaf_reaches_the_noise_floor_where_the_stft_recurrence_does_not():
