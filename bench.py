@@ -434,7 +434,14 @@ def also_rows(A, torch, sharding, args, fp32_peak, hbm_peak, hbm_src, local):
             sampler.stop()
             ms = total_ms / steps
             rf = roofline_of(wl, kern_ms, fp32_peak, hbm_peak, hbm_src)
-            rows.append({"workload": wl["name"], "ms_per_step": ms, "steps": steps,
+            cpu_port = None
+            if wl["algo"] >= 2 and wl["B"] <= 1024 and wl["frame"] == 512 and not args.no_cpu_baseline:
+                import numpy as np                              # the same filter through the C port, bounded sample
+                ns_ = cpu_sample_size(os.cpu_count() or 1, wl["B"])
+                v_, th_, _ = cpu_arm(np, far[:ns_].cpu().numpy(), mic[:ns_].cpu().numpy(), wl, 1, 1)
+                cpu_port = {"value": v_, "unit": "audio-s/s", "cores": th_, "kind": "port",
+                            "sample": f"first {ns_} utterances of this row's batch, 1 timed pass, C oracle (run_group_ols)"}
+            rows.append({"workload": wl["name"], "ms_per_step": ms, "steps": steps, "cpu_port": cpu_port,
                          "value": wl["B"] * wl["L"] / wl["sr"] / (ms * 1e-3), "unit": "audio-s/s",
                          "roofline": {"frac": rf["frac"], "achieved": rf["achieved"], "peak": rf["peak"], "unit": rf["unit"],
                                       "hbm_frac": rf["hbm"]["frac"], "kernel_ms": kern_ms},
@@ -456,6 +463,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS))
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--algo", type=int, default=None, choices=[0, 1, 2, 3],
+                    help="run the chosen config through another filter (2 / 3: the overlap-save PBFDAF); both arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true")
@@ -464,6 +473,9 @@ def main():
     ap.add_argument("--e2e-slice", type=int, default=128)
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
+    if args.algo is not None and args.algo != wl["algo"]:
+        wl = dict(wl, algo=args.algo, name=wl["name"] + " -- run through aec_cfg.algo = %d (%s)" % (
+            args.algo, ("nlms", "kalman", "ols-nlms", "ols-kalman")[args.algo]))
     if args.impl == "reference":
         return run_reference(args, wl)
     args.warmup = max(args.warmup, 3)
@@ -643,7 +655,7 @@ def main():
     hbm_peak, hbm_src = measured_peaks()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.algo is None:    # the captured traffic belongs to the config's own filter
         try:
             traffic = json.load(open(tpath)).get(f"config{args.config}")
         except Exception:

@@ -17,7 +17,7 @@ class OracleCfg(C.Structure):
     _fields_ = [("frame", C.c_int32), ("partitions", C.c_int32), ("algo", C.c_int32),
                 ("mu", C.c_float), ("delta", C.c_float), ("kalman_a", C.c_float),
                 ("kalman_lambda", C.c_float), ("kalman_c0", C.c_float), ("kalman_eps", C.c_float),
-                ("erle_skip_hops", C.c_int32)]
+                ("erle_skip_hops", C.c_int32), ("pb_lambda", C.c_float)]
 
 
 _lib = None
@@ -39,7 +39,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
 def make_cfg(cfg, erle_skip_hops: int = 0) -> OracleCfg:
     """cfg: oracle.aec_oracle.AecConfig"""
     return OracleCfg(cfg.frame, cfg.partitions, cfg.algo, cfg.mu, cfg.delta, cfg.kalman_a, cfg.kalman_lambda,
-                     cfg.kalman_c0, cfg.kalman_eps, erle_skip_hops)
+                     cfg.kalman_c0, cfg.kalman_eps, erle_skip_hops, getattr(cfg, "pb_lambda", 0.5))
 
 
 def stage1(far: np.ndarray, mic: np.ndarray, cfg, n_samples=None, want_echo: bool = True,

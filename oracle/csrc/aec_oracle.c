@@ -13,7 +13,7 @@
  * and are pinned through oracle/aec_oracle.py by the golden vectors in tests/golden/.
  * The FDAF recurrences (NLMS / Kalman) are BUILDER-AUTHORED: PARITY UNPINNED by the reference,
  * which contains no stage-1 filter.  They follow oracle/aec_oracle.py:fdaf_nlms / fdaf_kalman
- * statement by statement.
+ * (algos 0 / 1) and oracle/aec_oracle.py:pbfdaf_ols (algos 2 / 3, run_group_ols below) statement by statement.
  *
  * The reference computes each DFT as a dense [2K x N] convolution; this port uses an FFT
  * (same result to float32 rounding) so that the CPU baseline is not handicapped.  Since round 2 the transforms run
@@ -31,10 +31,11 @@
 typedef struct aec_oracle_cfg {
     int32_t frame;
     int32_t partitions;
-    int32_t algo; /* 0 NLMS, 1 Kalman */
+    int32_t algo; /* 0 NLMS, 1 Kalman (STFT domain); 2 NLMS step, 3 Kalman step (overlap-save PBFDAF) */
     float mu, delta;
     float kalman_a, kalman_lambda, kalman_c0, kalman_eps;
     int32_t erle_skip_hops;
+    float pb_lambda; /* algo 2: smoothing of the per-bin input power */
 } aec_oracle_cfg;
 
 typedef struct { float re, im; } cpx;
@@ -349,6 +350,225 @@ static void run_one(const plan* p, const aec_oracle_cfg* cfg, const float* far, 
     free(yr); free(yi); free(pw);
 }
 
+/* ---- overlap-save partitioned-block FDAF (algos 2 / 3), VL utterances at a time ----------------------------------
+ * Follows oracle/aec_oracle.py:pbfdaf_ols statement by statement (BUILDER-AUTHORED, PARITY UNPINNED like the other
+ * recurrences).  The recurrence crosses the transform every block, so there are no frames of one
+ * utterance to batch: the SIMD lanes are VL different utterances instead (layout [bin][VL] / [point][VL]), every
+ * transform and every statement of the update runs on all of them at once.  Lanes whose utterance is shorter (or absent)
+ * keep computing on zeros; nothing of theirs is stored. */
+static void rfft_lanes(const plan* p, float* restrict wre, float* restrict wim, float* restrict outr, float* restrict outi) {
+    const int m = p->m;
+    fft_c_v(p, wre, wim, -1);
+    for (int k = 0; k <= m; ++k) {
+        const int ka = k & (m - 1), kb = (m - k) & (m - 1);
+        const cpx w = p->tw_n[k];
+        const int edge = (k == 0 || k == m);
+#pragma omp simd
+        for (int l = 0; l < VL; ++l) {
+            const float ar = wre[ka * VL + l], ai = wim[ka * VL + l];
+            const float br = wre[kb * VL + l], bi = wim[kb * VL + l];
+            const float er = 0.5f * (ar + br), ei = 0.5f * (ai - bi);
+            const float orr = 0.5f * (ai + bi), oi = 0.5f * (br - ar);
+            outr[k * VL + l] = er + (orr * w.re - oi * w.im);
+            outi[k * VL + l] = edge ? 0.f : ei + (orr * w.im + oi * w.re);
+        }
+    }
+}
+
+/* inverse of rfft_lanes: time sample 2i in wre[i][.], 2i+1 in wim[i][.], scaled by 1/n */
+static void irfft_lanes(const plan* p, const float* restrict inr, const float* restrict ini, float* restrict wre,
+                        float* restrict wim) {
+    const int m = p->m;
+    const float sc = 1.0f / (float)p->n;
+    for (int k = 0; k < m; ++k) {
+        const cpx w = p->tw_n[k];
+        const float z = k == 0 ? 0.f : 1.f;          /* imaginary parts of DC / Nyquist do not exist */
+#pragma omp simd
+        for (int l = 0; l < VL; ++l) {
+            const float ar = inr[k * VL + l], ai = z * ini[k * VL + l];
+            const float br = inr[(m - k) * VL + l], bi = z * ini[(m - k) * VL + l];
+            const float e_r = ar + br, e_i = ai - bi;
+            const float dr = ar - br, di = ai + bi;
+            const float tr = dr * w.re + di * w.im, ti = di * w.re - dr * w.im;
+            wre[k * VL + l] = (e_r - ti) * sc;
+            wim[k * VL + l] = (e_i + tr) * sc;
+        }
+    }
+    fft_c_v(p, wre, wim, +1);
+}
+
+static void run_group_ols(const plan* p, const aec_oracle_cfg* cfg, const float* const* far, const float* const* mic,
+                          const int64_t* n, int64_t out_len_total, float* const* err, float* const* echo,
+                          float* const* erle_db) {
+    const int N = p->n, H = N / 2, K = H + 1, P = cfg->partitions, m = H;
+    const size_t row = (size_t)K * VL;
+    int64_t nblk[VL], nmax = 0;
+    for (int l = 0; l < VL; ++l) {
+        nblk[l] = far[l] ? n[l] / H : 0;
+        if (nblk[l] > nmax) nmax = nblk[l];
+    }
+    float* Wr = (float*)calloc((size_t)P * row, sizeof(float));
+    float* Wi = (float*)calloc((size_t)P * row, sizeof(float));
+    float* Xr = (float*)calloc((size_t)P * row, sizeof(float));     /* far-end ring: slot t mod P holds Xh of block t */
+    float* Xi = (float*)calloc((size_t)P * row, sizeof(float));
+    float* C = (float*)malloc(sizeof(float) * (size_t)P * row);
+    float* cx2 = (float*)malloc(sizeof(float) * (size_t)P * row);
+    float* pw = (float*)calloc(row, sizeof(float));
+    float* psi = (float*)calloc(row, sizeof(float));
+    float* rd = (float*)malloc(sizeof(float) * row);
+    float* Sr = (float*)malloc(sizeof(float) * row);                 /* Yhat, then E */
+    float* Si = (float*)malloc(sizeof(float) * row);
+    float* wre = (float*)malloc(sizeof(float) * (size_t)m * VL);
+    float* wim = (float*)malloc(sizeof(float) * (size_t)m * VL);
+    for (size_t i = 0; i < (size_t)P * row; ++i) C[i] = cfg->kalman_c0;
+    const float A = cfg->kalman_a, A2 = A * A, Q = (float)(1.0 - (double)A * (double)A);
+    const float klam = cfg->kalman_lambda, koml = 1.0f - klam, keps = cfg->kalman_eps;
+    const float mu = cfg->mu, delta = cfg->delta, lam = cfg->pb_lambda, oml = 1.0f - lam;
+    const int half = H / 2;                                          /* complex points per half of the 2H-sample vector */
+    double pm[VL] = {0}, pe[VL] = {0};
+
+    for (int64_t t = 0; t < nmax; ++t) {
+        /* Xh_0 = rfft([x_{t-1}, x_t]) into ring slot t mod P (the shift of the partitions is the ring index) */
+        for (int l = 0; l < VL; ++l) {
+            const int live = t < nblk[l];
+            const float* x = far[l];
+            for (int i = 0; i < half; ++i) {
+                wre[i * VL + l] = (live && t > 0) ? x[(t - 1) * H + 2 * i] : 0.f;
+                wim[i * VL + l] = (live && t > 0) ? x[(t - 1) * H + 2 * i + 1] : 0.f;
+                wre[(half + i) * VL + l] = live ? x[t * H + 2 * i] : 0.f;
+                wim[(half + i) * VL + l] = live ? x[t * H + 2 * i + 1] : 0.f;
+            }
+        }
+        rfft_lanes(p, wre, wim, Xr + (size_t)(t % P) * row, Xi + (size_t)(t % P) * row);
+        /* y = irfft(sum_p W_p Xh_p)[H:] */
+        memset(Sr, 0, sizeof(float) * row);
+        memset(Si, 0, sizeof(float) * row);
+        for (int q = 0; q < P; ++q) {
+            const size_t slot = (size_t)((t - q + 4 * (int64_t)P) % P) * row;
+            const float* restrict xr = Xr + slot;
+            const float* restrict xi = Xi + slot;
+            const float* restrict wr = Wr + (size_t)q * row;
+            const float* restrict wi = Wi + (size_t)q * row;
+#pragma omp simd
+            for (size_t j = 0; j < row; ++j) {
+                Sr[j] += wr[j] * xr[j] - wi[j] * xi[j];
+                Si[j] += wr[j] * xi[j] + wi[j] * xr[j];
+            }
+        }
+        irfft_lanes(p, Sr, Si, wre, wim);
+        /* e = d_t - y -> err; E = rfft([0_H, e]) */
+        for (int l = 0; l < VL; ++l) {
+            const int live = t < nblk[l];
+            for (int i = 0; i < half; ++i) {
+                float e0 = 0.f, e1 = 0.f;
+                if (live) {
+                    const int64_t s = t * H + 2 * i;
+                    const float y0 = wre[(half + i) * VL + l], y1 = wim[(half + i) * VL + l];
+                    const float d0 = mic[l][s], d1 = mic[l][s + 1];
+                    e0 = d0 - y0; e1 = d1 - y1;
+                    err[l][s] = e0; err[l][s + 1] = e1;
+                    if (echo && echo[l]) { echo[l][s] = y0; echo[l][s + 1] = y1; }
+                    if (t >= cfg->erle_skip_hops) {
+                        pe[l] += (double)e0 * e0 + (double)e1 * e1;
+                        pm[l] += (double)d0 * d0 + (double)d1 * d1;
+                    }
+                }
+                wre[i * VL + l] = 0.f; wim[i * VL + l] = 0.f;
+                wre[(half + i) * VL + l] = e0; wim[(half + i) * VL + l] = e1;
+            }
+        }
+        rfft_lanes(p, wre, wim, Sr, Si);                             /* E */
+        /* gradient constraint of partition c = t mod P, as it entered the block */
+        {
+            float* wr = Wr + (size_t)(t % P) * row;
+            float* wi = Wi + (size_t)(t % P) * row;
+            irfft_lanes(p, wr, wi, wre, wim);
+            memset(wre + (size_t)half * VL, 0, sizeof(float) * (size_t)half * VL);
+            memset(wim + (size_t)half * VL, 0, sizeof(float) * (size_t)half * VL);
+            rfft_lanes(p, wre, wim, wr, wi);
+        }
+        if (cfg->algo == 2) {
+            memset(rd, 0, sizeof(float) * row);
+            for (int q = 0; q < P; ++q) {                            /* sum_p |Xh_p|^2, newest partition first */
+                const size_t slot = (size_t)((t - q + 4 * (int64_t)P) % P) * row;
+                const float* restrict xr = Xr + slot;
+                const float* restrict xi = Xi + slot;
+#pragma omp simd
+                for (size_t j = 0; j < row; ++j) rd[j] += xr[j] * xr[j] + xi[j] * xi[j];
+            }
+#pragma omp simd
+            for (size_t j = 0; j < row; ++j) {
+                pw[j] = lam * pw[j] + oml * rd[j];
+                rd[j] = mu / (pw[j] + delta);                        /* g */
+            }
+            for (int q = 0; q < P; ++q) {
+                const size_t slot = (size_t)((t - q + 4 * (int64_t)P) % P) * row;
+                const float* restrict xr = Xr + slot;
+                const float* restrict xi = Xi + slot;
+                float* restrict wr = Wr + (size_t)q * row;
+                float* restrict wi = Wi + (size_t)q * row;
+#pragma omp simd
+                for (size_t j = 0; j < row; ++j) {
+                    const float gr = rd[j] * Sr[j], gi = rd[j] * Si[j];
+                    wr[j] += xr[j] * gr + xi[j] * gi;                /* conj(Xh_p) g E */
+                    wi[j] += xr[j] * gi - xi[j] * gr;
+                }
+            }
+        } else {
+#pragma omp simd
+            for (size_t j = 0; j < row; ++j) {
+                psi[j] = klam * psi[j] + koml * (Sr[j] * Sr[j] + Si[j] * Si[j]);
+                rd[j] = 0.f;
+            }
+            for (int q = 0; q < P; ++q) {
+                const size_t slot = (size_t)((t - q + 4 * (int64_t)P) % P) * row;
+                const float* restrict xr = Xr + slot;
+                const float* restrict xi = Xi + slot;
+                const float* restrict c = C + (size_t)q * row;
+                float* restrict cx = cx2 + (size_t)q * row;
+#pragma omp simd
+                for (size_t j = 0; j < row; ++j) {
+                    cx[j] = c[j] * (xr[j] * xr[j] + xi[j] * xi[j]);
+                    rd[j] += cx[j];
+                }
+            }
+#pragma omp simd
+            for (size_t j = 0; j < row; ++j) rd[j] = 1.0f / (rd[j] + psi[j] + keps);
+            for (int q = 0; q < P; ++q) {
+                const size_t slot = (size_t)((t - q + 4 * (int64_t)P) % P) * row;
+                const float* restrict xr = Xr + slot;
+                const float* restrict xi = Xi + slot;
+                float* restrict c = C + (size_t)q * row;
+                const float* restrict cx = cx2 + (size_t)q * row;
+                float* restrict wr = Wr + (size_t)q * row;
+                float* restrict wi = Wi + (size_t)q * row;
+#pragma omp simd
+                for (size_t j = 0; j < row; ++j) {
+                    const float gs = c[j] * rd[j];
+                    const float gr = gs * xr[j], gi = -gs * xi[j];
+                    const float nr = A * (wr[j] + gr * Sr[j] - gi * Si[j]);
+                    const float ni = A * (wi[j] + gr * Si[j] + gi * Sr[j]);
+                    wr[j] = nr; wi[j] = ni;
+                    c[j] = A2 * (1.0f - cx[j] * rd[j]) * c[j] + Q * (nr * nr + ni * ni);
+                }
+            }
+        }
+    }
+    for (int l = 0; l < VL; ++l) {
+        if (!far[l]) continue;
+        for (int64_t i = nblk[l] * H; i < out_len_total; ++i) {
+            err[l][i] = 0.f;
+            if (echo && echo[l]) echo[l][i] = 0.f;
+        }
+        if (erle_db && erle_db[l]) {
+            double a = pm[l] < 1e-20 ? 1e-20 : pm[l], b = pe[l] < 1e-20 ? 1e-20 : pe[l];
+            *erle_db[l] = (float)(10.0 * log10(a / b));
+        }
+    }
+    free(Wr); free(Wi); free(Xr); free(Xi); free(C); free(cx2); free(pw); free(psi); free(rd); free(Sr); free(Si);
+    free(wre); free(wim);
+}
+
 /* Batch entry.  Buffers are host float32; n_samples nullable.  n_threads <= 0 -> all cores.
  * Returns the number of threads used (>= 1) or a negative error. */
 int aec_oracle_stage1_f32(const float* far, const float* mic, float* err, float* echo, float* erle_db,
@@ -357,11 +577,41 @@ int aec_oracle_stage1_f32(const float* far, const float* mic, float* err, float*
     if (!far || !mic || !err || !cfg || B < 0 || L < 0) return -1;
     if (cfg->frame != 512 && cfg->frame != 1024) return -2;
     if (cfg->partitions < 1) return -1;
+    if (cfg->algo < 0 || cfg->algo > 3) return -2;
     plan* p = plan_create(cfg->frame);
     int used = 1;
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_max_threads();
     used = n_threads;
+#endif
+    if (cfg->algo >= 2) {                 /* overlap-save filters: groups of VL utterances, one group per task */
+        const int64_t groups = (B + VL - 1) / VL;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+#endif
+        for (int64_t g = 0; g < groups; ++g) {
+            const float *f[VL], *d[VL];
+            float *e[VL], *y[VL], *r[VL];
+            int64_t nn[VL];
+            for (int l = 0; l < VL; ++l) {
+                const int64_t b = g * VL + l;
+                const int on = b < B;
+                int64_t n = on ? (n_samples ? n_samples[b] : L) : 0;
+                if (n < 0) n = 0;
+                if (n > L) n = L;
+                nn[l] = n;
+                f[l] = on ? far + b * in_stride : NULL;
+                d[l] = on ? mic + b * in_stride : NULL;
+                e[l] = on ? err + b * out_stride : NULL;
+                y[l] = (on && echo) ? echo + b * out_stride : NULL;
+                r[l] = (on && erle_db) ? erle_db + b : NULL;
+            }
+            run_group_ols(p, cfg, f, d, nn, L, e, echo ? y : NULL, erle_db ? r : NULL);
+        }
+        plan_destroy(p);
+        return used;
+    }
+#ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
 #endif
     for (int64_t b = 0; b < B; ++b) {

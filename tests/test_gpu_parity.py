@@ -370,10 +370,11 @@ def test_create_h5_train_end_to_end_on_the_gpu(tmp_path, algo_flag):
 
 def test_full_batch_against_the_c_port_on_random_utterances():
     """at the full config-2 and config-3 batch sizes, 32 randomly chosen utterances of the batch
-    against the float32 C port (fast enough for 10 s utterances) instead of relying on batch-invariance transitivity"""
+    against the float32 C port (fast enough for 10 s utterances) instead of relying on batch-invariance transitivity;
+    the config-2 batch also through the overlap-save filters (algos 2 / 3; the port runs them eight utterances abreast)"""
     from oracle import c_oracle as CO
     rng = np.random.default_rng(11)
-    for (B, P, algo, L) in [(1024, 4, 0, 160000), (4096, 16, 1, 160000)]:
+    for (B, P, algo, L) in [(1024, 4, 0, 160000), (4096, 16, 1, 160000), (1024, 4, 2, 160000), (1024, 4, 3, 160000)]:
         base = synth.make_batch(500, 16, L, rir_len=min(P * 256, 2048))
         gains = (0.25 + 0.75 * rng.random(B)).astype(np.float32)
         far = torch.from_numpy(base["far"]).cuda()[torch.arange(B, device="cuda") % 16] * torch.from_numpy(gains).cuda()[:, None]

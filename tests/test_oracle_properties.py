@@ -68,6 +68,30 @@ def test_c_oracle_matches_numpy_oracle(algo, P, L):
         assert (c["err"][b, m:] == 0).all()
 
 
+@pytest.mark.parametrize("algo,P,L,frame", [(2, 4, 16123, 512), (3, 4, 16000, 512), (3, 16, 12000, 512), (2, 8, 8000, 512),
+                                            (2, 1, 4000, 512), (3, 8, 20000, 1024), (2, 2, 300, 512)])
+def test_c_oracle_overlap_save_matches_numpy_oracle(algo, P, L, frame):
+    """the port runs the overlap-save filters eight utterances abreast (SIMD lanes = utterances): 11 ragged utterances
+    = one full group and a partial one, every lane against the float64 oracle run on its utterance alone"""
+    H = frame // 2
+    cfg = O.AecConfig(frame=frame, partitions=P, algo=algo, delta=1e-6 * frame)
+    B = 11
+    d = synth.make_batch(0, B, L, rir_len=P * H)
+    ns = np.array([L, L - 1, max(L - 777, 0)] + [max(L - 100 * i, 0) for i in range(B - 3)])
+    r = O.stage1(d["far"], d["mic"], cfg, n_samples=ns, erle_skip=8 * H)
+    c = CO.stage1(d["far"], d["mic"], cfg, n_samples=ns, erle_skip_hops=8)
+    n = r["err"].shape[1]
+    assert np.abs(c["err"][:, :n] - r["err"]).max() < 2e-5
+    assert np.abs(c["echo"][:, :n] - r["echo"]).max() < 2e-5
+    assert np.abs(c["erle_db"] - r["erle_db"]).max() < 1e-3
+    for b in range(B):
+        m = int(ns[b]) // H * H
+        assert (c["err"][b, m:] == 0).all() and (c["echo"][b, m:] == 0).all()
+    # a lane does not see its neighbours: utterance 4 alone gives the same bits
+    alone = CO.stage1(d["far"][4:5], d["mic"][4:5], cfg, n_samples=ns[4:5], erle_skip_hops=8)
+    assert np.array_equal(alone["err"][0], c["err"][4]) and alone["erle_db"][0] == c["erle_db"][4]
+
+
 def test_ragged_equals_alone():
     d = synth.make_batch(7, 2, 6000)
     ns = np.array([6000, 3333])
