@@ -24,10 +24,12 @@ How a run is organised (the reference is one serial loop: decode 4 wavs, write, 
 all three overlapped, three buffer sets cycling.  With ``torch.distributed`` initialised each rank converts a
 contiguous shard of the SORTED id list on its own GPU (LOCAL_RANK) and rank 0 writes the merged list.
 
-``h5py`` is required to write the reference's ``.ex`` (HDF5) files.  It is absent from the build image, so the
-import is deferred, and ``NpzStore`` -- same ``File / create_group / create_dataset / close`` surface, one
-uncompressed ``.npz`` per file with ``group/key`` member names -- can stand in (``h5=NpzStore()``) where the
-pipeline is to be run and timed without it; the files it writes are NOT readable by the reference's readers.
+The ``.ex`` files are HDF5.  ``h5py`` is used when it is installed (the reference's own writer); it is absent from the
+build image, and then ``h5lite`` -- this package's own writer of the HDF5 subset those files need (superblock v0,
+symbol-table groups, contiguous float32 datasets; h5lite.py) -- writes them, so the generators produce files the
+reference's readers open either way.  ``h5=`` selects a container explicitly: ``h5lite``, the ``h5py`` module, or the
+two non-HDF5 stand-ins kept for measurements (``NpzStore``: one uncompressed ``.npz`` per file; ``RawStore``: raw
+bytes + JSON index), whose files are NOT readable by the reference's readers.
 """
 from __future__ import annotations
 
@@ -181,12 +183,14 @@ def default_runner(cfg=None, slice_utterances: int = 128, device: Optional[int] 
 
 
 def _h5py():
+    """the module whose ``File(name, 'w')`` writes the ``.ex`` files: h5py when installed, else this package's own
+    HDF5 writer (same call surface, same names / shapes / types / values on disk, contiguous storage)"""
     try:
         import h5py  # type: ignore
-    except ImportError as e:  # pragma: no cover - depends on the box
-        raise ImportError("writing the reference's .ex (HDF5) files needs h5py, which is not installed "
-                          "(pass h5=NpzStore() to run the pipeline with the stand-in container)") from e
-    return h5py
+        return h5py
+    except ImportError:  # pragma: no cover - depends on the box
+        from . import h5lite
+        return h5lite
 
 
 class _NpzGroup:

@@ -325,6 +325,27 @@ def test_runner_buffers_are_page_locked_and_pageable_inputs_are_staged():
     run.close()
 
 
+class _ExFile:
+    """`z[key]` -> array for an .ex (HDF5) file: h5py when present, else h5lite's reader"""
+
+    def __init__(self, path):
+        try:
+            import h5py  # type: ignore
+            self.f = h5py.File(path, "r")
+        except ImportError:
+            from acoustic_echo_cancellation_b200 import h5lite
+            self.f = h5lite.File(path, "r")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.f.close()
+
+    def __getitem__(self, key):
+        return np.array(self.f[key])
+
+
 @pytest.mark.parametrize("algo_flag", [None, "ols-kalman"])
 def test_create_h5_train_end_to_end_on_the_gpu(tmp_path, algo_flag):
     """wav files -> create_h5 (decode | stage 1 | write, default CUDA runner, NpzStore container) -> files whose
@@ -355,11 +376,18 @@ def test_create_h5_train_end_to_end_on_the_gpu(tmp_path, algo_flag):
                                                      str(list_dir), "--stage1_algo", algo_flag, "--stage1_partitions", "4"])
         kw["runner"] = wav2h5.runner_from_args(a)
         cfg = A.Stage1Config(algo=A.ALGO_PBFKF, partitions=4)
-    paths = wav2h5.create_h5(args, batch=8, h5=wav2h5.NpzStore(), stats=st, **kw)
+    # the plain run writes the stand-in npz container, the ols-kalman run the DEFAULT one: real HDF5 (.ex) through
+    # h5py when installed, else through the package's own writer (h5lite)
+    from acoustic_echo_cancellation_b200 import h5lite
+    if algo_flag:
+        paths = wav2h5.create_h5(args, batch=8, stats=st, **kw)
+        assert all(h5lite.is_hdf5(p) for p in paths)
+    else:
+        paths = wav2h5.create_h5(args, batch=8, h5=wav2h5.NpzStore(), stats=st, **kw)
     assert len(paths) == 37 and st["pcm16_batches"] == 5 and st["float32_batches"] == 0
     for p in paths[::6]:
         i = p.split("tr_")[-1][:-3]
-        with np.load(p) as z:
+        with (_ExFile(p) if algo_flag else np.load(p)) as z:
             for key in wav2h5.KEYS:
                 assert np.array_equal(z[key], sig[(i, key)])
             dev = A.stage1_aec(_cuda(sig[(i, "farend_speech")][None]), _cuda(sig[(i, "nearend_mic")][None]), cfg,

@@ -12,8 +12,10 @@ What is and is not measured
   which no box here holds; the per-utterance work is the same and throughput is reported per utterance.
 * Files go to --root (default /dev/shm when it has room, else the system temp dir): the page cache / tmpfs, not a
   disk array -- this measures the pipeline (decode, PCIe, kernel, container write), not a storage system.
-* h5py is absent from the image: the container is wav2h5.RawStore (the datasets' bytes + an index per utterance,
-  same keys) unless h5py imports; the JSON line says which.
+* Container (`--container`): `auto` = h5py when it imports, else h5lite -- the package's own HDF5 writer, so the output
+  IS the reference's `.ex` format (h5py / libhdf5 are absent from the image); `raw` = wav2h5.RawStore (the datasets'
+  bytes + an index per utterance, same keys: the container of the round-2 tables in profiles/r2_config5_files_*);
+  the JSON line says which, and one output file is read back and checked after the timed region.
 * `reference_loop`: the reference's loop shape on ONE core (its scripts are single-threaded) over a bounded sample --
   scipy decode x 4 + one container write per utterance, without any filter (the reference has none) and, second
   figure, with the single-threaded C port of the stage-1 filter in the loop.
@@ -92,6 +94,7 @@ def main():
     ap.add_argument("--decode-threads", type=int, default=0, help="0 = cores available to this rank")
     ap.add_argument("--write-threads", type=int, default=0)
     ap.add_argument("--root", default=None)
+    ap.add_argument("--container", default="auto", choices=["auto", "raw"])
     ap.add_argument("--ref-sample", type=int, default=48)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -121,11 +124,15 @@ def main():
         link_ids(pool_dir, train_dir, args.pool, 0, total)
     if world > 1:
         dist.barrier()
-    try:
-        import h5py  # type: ignore
-        store, container = h5py, "h5py"
-    except ImportError:
-        store, container = wav2h5.RawStore(), "RawStore (raw stand-in container: h5py is not installed)"
+    if args.container == "raw":
+        store, container = wav2h5.RawStore(), "RawStore (raw stand-in container)"
+    else:
+        try:
+            import h5py  # type: ignore
+            store, container = h5py, "h5py"
+        except ImportError:
+            from acoustic_echo_cancellation_b200 import h5lite
+            store, container = h5lite, "h5lite (HDF5 written by the package itself: h5py is not installed)"
     ns = types.SimpleNamespace(train_path=train_dir, h5_path=h5_dir, list_path=list_dir, sr=sr)
     runner = wav2h5.default_runner(slice_utterances=128, device=local)
     # warm-up: CUDA context, page-locked buffers, kernel load (a small separate run into a scratch folder)
@@ -149,6 +156,11 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     secs = float(dt[0])
     ok = len(merged) == total and all(os.path.exists(p) for p in merged[:: max(1, total // 64)])
+    if ok and rank == 0 and args.container != "raw" and container.startswith("h5lite"):
+        from acoustic_echo_cancellation_b200 import h5lite      # one output file read back: keys, shapes, finite values
+        with h5lite.File(merged[len(merged) // 2], "r") as r:
+            ok = (set(r) == set(wav2h5.KEYS) | {"stage1_error", "stage1_echo"} and r["stage1_error"].shape == (n,)
+                  and bool(np.isfinite(r["stage1_error"][:]).all()) and r["nearend_mic"].dtype == np.float32)
     if rank == 0:
         line = {"workload": "configs[4] shape: wav dir -> stage 1 (4-partition FDAF-NLMS) -> one output file per utterance + "
                             "tr_list.txt, sharded over the ranks", "n_gpus": world, "utterances": total,
