@@ -88,6 +88,7 @@ SIGNATURES = {
     "aec_wav_probe": (C.c_int, [C.c_char_p, C.POINTER(WavInfo)]),
     "aec_wav_probe_batch": (C.c_int, [C.POINTER(C.c_char_p), _I64, C.POINTER(WavInfo), _I32]),
     "aec_wav_read_pcm16_batch": (C.c_int, [C.POINTER(C.c_char_p), _I64, _P, _I64, _I64, _P, _I32, _I32]),
+    "aec_ex_write_batch": (C.c_int, [C.POINTER(C.c_char_p), _I64, _I32, C.POINTER(C.c_char_p), C.POINTER(_P), _P, _P, _I32]),
     "aec_stft": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P]),
     "aec_istft": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P]),
     "aec_features": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I32, C.c_float, C.c_float, _P]),

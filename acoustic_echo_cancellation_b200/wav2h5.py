@@ -390,9 +390,46 @@ def _signal(b: ingest.DecodedBatch, key: str, j: int) -> np.ndarray:
     return b.signals[{"farend_speech": "__far__", "nearend_mic": "__mic__"}.get(key, key)][j]
 
 
+def write_ex_batch(paths: Sequence[str], names: Sequence[str], rows: Sequence[Sequence[np.ndarray]], threads: int = 8):
+    """``rows[f][d]`` (1-D float32, or int16 PCM stored as float32 = s / 32768) -> dataset ``names[d]`` of the HDF5 file
+    ``paths[f]``; the native batched form of the reference's per-utterance writer block (train_wav2h5.py:35-44),
+    ``aec_ex_write_batch``."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    nf, nd = len(paths), len(names)
+    keep = []                                       # arrays that had to be made contiguous / converted stay alive
+    ptrs = (C.c_void_p * (nf * nd))()
+    lens = np.zeros(nf * nd, dtype=np.int64)
+    fmts = np.zeros(nd, dtype=np.int32)
+    for d in range(nd):
+        if nf and all(rows[f][d].dtype == np.int16 for f in range(nf)):
+            fmts[d] = 1
+    for f in range(nf):
+        for d in range(nd):
+            a = rows[f][d]
+            want = np.int16 if fmts[d] == 1 else np.float32
+            if a.dtype != want:
+                a = ingest.as_float32(a)
+            if a.ndim != 1 or not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a).reshape(-1)
+            keep.append(a)
+            ptrs[f * nd + d] = a.ctypes.data
+            lens[f * nd + d] = a.shape[0]
+    cpaths = (C.c_char_p * nf)(*[os.fsencode(p) for p in paths])
+    cnames = (C.c_char_p * nd)(*[n.encode() for n in names])
+    _lib.check(lib.aec_ex_write_batch(cpaths, nf, nd, cnames, ptrs, lens.ctypes.data, fmts.ctypes.data, int(threads)),
+               "aec_ex_write_batch")
+
+
 def create_h5_train(args, runner: Optional[Callable] = None, batch: int = 256, h5=None, decode_threads: int = 8,
-                    write_threads: int = 8, pinned: Optional[bool] = None, stats: Optional[dict] = None):
-    """``create_h5(args)`` of train_wav2h5.py with stage 1 inserted.  One ``tr_<idx>.ex`` per utterance."""
+                    write_threads: int = 8, pinned: Optional[bool] = None, stats: Optional[dict] = None,
+                    native_writer: bool = True):
+    """``create_h5(args)`` of train_wav2h5.py with stage 1 inserted.  One ``tr_<idx>.ex`` per utterance.  With the
+    package's own HDF5 container (``h5lite``: the default where h5py is not installed) the files of a batch are
+    written by one native call (``aec_ex_write_batch``); ``native_writer=False`` keeps the per-file Python writer."""
     h5 = h5 or _h5py()
     ids, rank = _shard(list_utterance_ids(args.train_path))
     os.makedirs(os.path.join(args.h5_path, "tr"), exist_ok=True)
@@ -414,6 +451,18 @@ def create_h5_train(args, runner: Optional[Callable] = None, batch: int = 256, h
         for f in futs:
             f.result()
 
+    def emit_native(k, chunk, b, errs, echos):
+        # the whole batch in ONE C call (aec_ex_write_batch: C++ threads, int16 -> float32 on the way out, no
+        # interpreter between the files); same bytes as write_one through h5lite
+        names = KEYS + ("stage1_error", "stage1_echo")
+        rows = [[_signal(b, key, j) for key in KEYS] + [errs[j], echos[j]] for j in range(len(chunk))]
+        write_ex_batch([os.path.join(args.h5_path, "tr", "tr_" + idx + ".ex") for idx in chunk], names, rows,
+                       threads=max(1, write_threads))
+
+    from . import h5lite
+
+    if h5 is h5lite and native_writer:
+        emit = emit_native                                               # noqa: F811
     st = eng.run(ids, _train_paths(args.train_path), emit)
     pool.shutdown()
     if stats is not None:

@@ -188,6 +188,19 @@ int aec_wav_probe_batch(const char* const* paths, int64_t n, aec_wav_info* infos
 int aec_wav_read_pcm16_batch(const char* const* paths, int64_t n, int16_t* dst, int64_t row_stride,
                              int64_t row_samples, int64_t* frames, int32_t expect_rate, int32_t threads);
 
+/* Batched writer of the per-utterance training files (host code): replaces, for a whole batch, the
+ * `h5py.File(tr_filename, 'w')` / `create_dataset(key, data=x.astype(np.float32), shape=x.shape, chunks=True)` x 4 /
+ * `close()` block of Stage2_lhm/generate_h5files/train_wav2h5.py:35-44.  File f (paths[f]) becomes an HDF5 file whose
+ * root group holds n_datasets (<= 8) one-dimensional float32 datasets names[d] of lens[f * n_datasets + d] samples
+ * taken from data[f * n_datasets + d]; formats[d] (nullable = all 0) says what the source is: 0 = float32, stored as it
+ * is; 1 = 16-bit PCM, stored as float32 = sample / 32768 (librosa's scaling, train_wav2h5.py:20-23).  `threads` C++
+ * threads share the files.  Format: superblock v0, symbol-table root group, contiguous storage -- byte-identical to
+ * acoustic_echo_cancellation_b200/h5lite.py (which documents it and reads it back); every libhdf5 / h5py opens it.
+ * Returns AEC_EINVAL for bad arguments (duplicate / empty / '/'-containing names, > 8 datasets), AEC_EIO when a file
+ * cannot be created or written (the other files of the batch are still attempted). */
+int aec_ex_write_batch(const char* const* paths, int64_t n_files, int32_t n_datasets, const char* const* names,
+                       const void* const* data, const int64_t* lens, const int32_t* formats, int32_t threads);
+
 /* STFT analysis on DEVICE buffers: replaces ConvSTFT(frame, frame/2, frame, 'hann', 'complex')
  * .forward (Stage2_lhm/scripts/network/attention_ccrn.py:45-52).
  *   x [B][in_stride] -> spec [B][2K][T], K = frame/2+1, T = aec_num_frames(L): channels

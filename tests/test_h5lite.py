@@ -291,3 +291,61 @@ def test_reference_readers_open_the_generated_files(tmp_path):
         for k in wav2h5.KEYS:
             assert np.array_equal(z[f"val/{g}/{k}"], f32(data[(idx, k)]))
         assert int(z[f"val/{g}/n_samples"]) == len(data[(idx, "nearend_speech")])
+
+
+def test_native_batch_writer_is_byte_identical_to_h5lite(tmp_path):
+    """aec_ex_write_batch (C++ threads, csrc/aec_exio.cu) and the Python writer are two implementations of the same
+    layout: same bytes for float32 and 16-bit PCM sources, odd lengths (alignment padding), empty datasets, names in
+    any creation order; bad arguments are refused, an unwritable path is an I/O error"""
+    from acoustic_echo_cancellation_b200 import _lib, ingest
+
+    rng = np.random.default_rng(5)
+    names = ("nearend_speech", "nearend_mic", "farend_speech", "echo", "stage1_error", "stage1_echo")
+    lens = [160000, 1001, 1, 0, 255, 4097, 7]
+    rows, paths = [], []
+    for f, n in enumerate(lens):
+        row = [(rng.standard_normal(n) * 3000).astype(np.int16) for _ in range(4)]
+        row += [rng.standard_normal(max(n - 3, 0)).astype(np.float32), rng.standard_normal(n).astype(np.float32)]
+        rows.append(row)
+        paths.append(str(tmp_path / f"native_{f}.ex"))
+    wav2h5.write_ex_batch(paths, names, rows, threads=3)
+    for f, p in enumerate(paths):
+        q = str(tmp_path / f"python_{f}.ex")
+        with h5lite.File(q, "w") as w:
+            for k, a in zip(names, rows[f]):
+                a = ingest.as_float32(a)
+                w.create_dataset(k, data=a, shape=a.shape, chunks=True)
+        assert open(p, "rb").read() == open(q, "rb").read(), f
+        found = _walk_file(p)
+        assert set(found) == set(names)
+        assert np.array_equal(found["echo"], rows[f][3].astype(np.float32) / np.float32(32768))
+    # float32-only rows, two datasets, reverse-sorted creation order
+    a, b = rng.standard_normal(33).astype(np.float32), rng.standard_normal(5).astype(np.float32)
+    p = str(tmp_path / "two.ex")
+    wav2h5.write_ex_batch([p], ("zeta", "alpha"), [[a, b]], threads=1)
+    with h5lite.File(str(tmp_path / "two_py.ex"), "w") as w:
+        w.create_dataset("zeta", data=a)
+        w.create_dataset("alpha", data=b)
+    assert open(p, "rb").read() == open(tmp_path / "two_py.ex", "rb").read()
+    with h5lite.File(p, "r") as r:
+        assert list(r) == ["alpha", "zeta"] and np.array_equal(r["zeta"][:], a)
+    with pytest.raises(_lib.AecError):
+        wav2h5.write_ex_batch([p], ("same", "same"), [[a, b]])
+    with pytest.raises(_lib.AecError):
+        wav2h5.write_ex_batch([p], ("a/b", "c"), [[a, b]])
+    with pytest.raises(_lib.AecError):
+        wav2h5.write_ex_batch([p], tuple(f"d{i}" for i in range(9)), [[a] * 9])
+    with pytest.raises(_lib.AecError):
+        wav2h5.write_ex_batch([str(tmp_path / "no_such_dir" / "x.ex")], ("a",), [[a]])
+
+
+def test_create_h5_train_native_and_python_writers_agree(tmp_path):
+    wav_dir, val_dir, h5_dir, list_dir, ids, data, vdata = _make_sets(tmp_path)
+    out = {}
+    for native in (True, False):
+        d = tmp_path / f"h5_{native}"
+        d.mkdir()
+        args = types.SimpleNamespace(train_path=str(wav_dir), h5_path=str(d), list_path=str(list_dir), sr=16000)
+        paths = wav2h5.create_h5_train(args, runner=_fake_runner, batch=4, h5=h5lite, native_writer=native)
+        out[native] = {os.path.basename(p): open(p, "rb").read() for p in paths}
+    assert out[True] == out[False] and len(out[True]) == len(ids)
