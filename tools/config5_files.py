@@ -95,7 +95,7 @@ def main():
     ap.add_argument("--write-threads", type=int, default=0)
     ap.add_argument("--root", default=None)
     ap.add_argument("--container", default="auto", choices=["auto", "raw"])
-    ap.add_argument("--repeats", type=int, default=3, help="timed conversions of the set; the last one is the headline")
+    ap.add_argument("--repeats", type=int, default=3, help="timed conversions of the set; the median is the headline (phase seconds: last run)")
     ap.add_argument("--ref-sample", type=int, default=48)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,8 +149,8 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     runs = []
-    for rep in range(max(1, args.repeats)):                  # the whole conversion, `--repeats` times; the LAST is reported
-        if rep:                                               # as the headline, every wall time in `wall_s_runs`
+    for rep in range(max(1, args.repeats)):                  # the whole conversion, `--repeats` times; the MEDIAN is the
+        if rep:                                               # headline, every wall time is in `wall_s_runs`
             if world > 1:
                 dist.barrier()
             if rank == 0:
@@ -165,7 +165,7 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         runs.append(float(dt[0]))
-    secs = runs[-1]
+    secs = sorted(runs)[len(runs) // 2]                      # headline = the median run
     ok = len(merged) == total and all(os.path.exists(p) for p in merged[:: max(1, total // 64)])
     if ok and rank == 0 and args.container != "raw" and container.startswith("h5lite"):
         from acoustic_echo_cancellation_b200 import h5lite      # one output file read back: keys, shapes, finite values
