@@ -576,9 +576,26 @@ def build_parser(kind: str) -> argparse.ArgumentParser:
     p.add_argument("--sr", type=int, default=16000)
     # not in the reference (which has no stage 1): which filter produces stage1_error / stage1_echo
     p.add_argument("--stage1_algo", choices=sorted(STAGE1_ALGOS), default="nlms",
-                   help="nlms / kalman: STFT-domain recurrence; ols-nlms / ols-kalman: overlap-save PBFDAF (frame 512, <= 4 partitions)")
+                   help="nlms / kalman: STFT-domain recurrence; ols-nlms / ols-kalman: overlap-save PBFDAF (frame 512, 1-16 partitions)")
     p.add_argument("--stage1_partitions", type=int, default=4)
+    # not in the reference (which always writes through h5py): who writes the .ex (HDF5) files
+    p.add_argument("--ex_writer", choices=["auto", "h5py", "native"], default="auto",
+                   help="auto: h5py when installed (chunked storage, as the reference writes), else the package's own HDF5 "
+                        "writer; native: the package's writer even when h5py is there (contiguous storage, batched C++ "
+                        "writer for the per-utterance training files)")
     return p
+
+
+def container_from_args(args):
+    """the module whose ``File`` writes the .ex files, per ``--ex_writer`` (None -> the default of ``_h5py()``)"""
+    which = getattr(args, "ex_writer", "auto")
+    if which == "native":
+        from . import h5lite
+        return h5lite
+    if which == "h5py":
+        import h5py  # type: ignore
+        return h5py
+    return None
 
 
 STAGE1_ALGOS = {"nlms": 0, "kalman": 1, "ols-nlms": 2, "ols-kalman": 3}
@@ -596,4 +613,5 @@ def runner_from_args(args) -> Optional[Callable]:
 def main(kind: str = "train", argv=None):
     args = build_parser(kind).parse_args(argv)
     os.makedirs(args.h5_path, exist_ok=True)
-    return {"train": create_h5_train, "test": create_h5_test, "val": create_h5_val}[kind](args, runner=runner_from_args(args))
+    return {"train": create_h5_train, "test": create_h5_test, "val": create_h5_val}[kind](
+        args, runner=runner_from_args(args), h5=container_from_args(args))

@@ -349,3 +349,10 @@ def test_create_h5_train_native_and_python_writers_agree(tmp_path):
         paths = wav2h5.create_h5_train(args, runner=_fake_runner, batch=4, h5=h5lite, native_writer=native)
         out[native] = {os.path.basename(p): open(p, "rb").read() for p in paths}
     assert out[True] == out[False] and len(out[True]) == len(ids)
+
+
+def test_ex_writer_flag_selects_the_container():
+    a = wav2h5.build_parser("train").parse_args(["--ex_writer", "native"])
+    assert wav2h5.container_from_args(a) is h5lite
+    assert wav2h5.container_from_args(wav2h5.build_parser("val").parse_args([])) is None
+    assert wav2h5.container_from_args(types.SimpleNamespace()) is None            # the reference's own argparse namespace
