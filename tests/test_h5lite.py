@@ -356,3 +356,47 @@ def test_ex_writer_flag_selects_the_container():
     assert wav2h5.container_from_args(a) is h5lite
     assert wav2h5.container_from_args(wav2h5.build_parser("val").parse_args([])) is None
     assert wav2h5.container_from_args(types.SimpleNamespace()) is None            # the reference's own argparse namespace
+
+
+def test_random_trees_round_trip_property():
+    """hypothesis: random group trees (names incl. UTF-8, shared prefixes, up to 40 members per group -> several
+    symbol-table nodes), random dtypes / shapes -> the structural walk and the reader both return what went in"""
+    hyp = pytest.importorskip("hypothesis")
+    import tempfile
+
+    from hypothesis import strategies as st
+
+    names = st.text(alphabet=st.characters(blacklist_characters="/\x00", blacklist_categories=("Cs",)), min_size=1, max_size=12)
+    dtypes = st.sampled_from([np.float32, np.float64, np.int16, np.int32, np.int64, np.uint8])
+    shapes = st.one_of(st.tuples(st.integers(0, 40)), st.tuples(st.integers(0, 5), st.integers(1, 4)))
+    leaf = st.tuples(dtypes, shapes, st.integers(0, 2 ** 31 - 1))
+    tree = st.dictionaries(names, st.one_of(leaf, st.dictionaries(names, leaf, max_size=12)), max_size=40)
+
+    def build(w, spec, prefix, ref):
+        for name, v in spec.items():
+            if isinstance(v, dict):
+                build(w.create_group(name), v, prefix + name + "/", ref)
+            else:
+                dt, shape, seed = v
+                a = (np.random.default_rng(seed).standard_normal(shape) * 100).astype(dt)
+                w.create_dataset(name, data=a)
+                ref[prefix + name] = a
+
+    @hyp.settings(max_examples=40, deadline=None)
+    @hyp.given(tree)
+    def check(spec):
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "t.h5")
+            ref = {}
+            with h5lite.File(path, "w") as w:
+                build(w, spec, "", ref)
+            found = _walk_file(path)
+            assert set(found) == set(ref)
+            with h5lite.File(path, "r") as r:
+                assert sorted(r) == sorted(spec)
+                for k, a in ref.items():
+                    assert found[k].dtype == a.dtype and np.array_equal(found[k], a)
+                    got = r[k][...]
+                    assert got.shape == a.shape and got.dtype == a.dtype and np.array_equal(got, a)
+
+    check()
