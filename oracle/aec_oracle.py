@@ -20,7 +20,11 @@ Parity status
   repository contains no stage-1 adaptive filter at all (no FDAF/NLMS/Kalman/ERLE
   code).  The recurrences below are BUILDER-AUTHORED, frozen in DESIGN.md
   ("Frozen recurrence"), and must never be described as "the reference
-  implementation".
+  implementation".  They are instances of published filters (DESIGN.md section 2, "Lineage":
+  Avargel & Cohen 2007 for the cross-band-free STFT-domain model, Enzner & Vary 2006 / Kuech et al.
+  2014 for the diagonal frequency-domain Kalman step, Soo & Pang 1990 with the alternated constraint
+  of Joho & Moschytz 2000 for ``pbfdaf_ols``), written out here with fixed constants; no code of
+  theirs was available to check against.
 
 All functions are plain numpy.  ``dtype=np.float64`` is the arbiter for parity
 tests (the CUDA path computes in float32; tolerance 1e-4 max-abs on the
