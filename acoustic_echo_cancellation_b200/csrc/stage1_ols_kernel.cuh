@@ -229,6 +229,12 @@ __global__ void __launch_bounds__(OlsShape<P>::NT) __maxnreg__(REGS) stage1_ols_
         dbg_sm[warp][11] = clock64();
     }
 #endif
+    // tuning (aec_cfg.stagger_ns > 0): start-up skew between the utterances that share an SM, so that the issue-bound
+    // update phase of one meets the latency-bound transform phase of another instead of all of them running in step
+    if (prm.stagger_ns > 0) {
+        const unsigned slot = (unsigned)(blockIdx.x / (unsigned)prm.num_sms) & 7u;
+        if (slot) __nanosleep(slot * (unsigned)prm.stagger_ns);
+    }
     __syncthreads();
     const int fw = *fft_warp_s;
 
